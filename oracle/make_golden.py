@@ -1,0 +1,191 @@
+"""Generates tests/golden/*.npz by running the REFERENCE ITSELF in the build container.
+TEST INFRASTRUCTURE ONLY.  Run:  python -m oracle.make_golden  (needs /root/reference).
+
+The reference has no tests or golden vectors, so these fixtures are
+produced from its own functions:
+
+* ``sample_representative_frames`` / ``sample_frames_uniform``
+  (/root/reference/src/preprocessing/datautils/utils.py:31,96) imported unmodified;
+* ``sample_frame_indices`` (extract_features.py:32-39) compiled from its AST node;
+* the MIF expression ``scores[::ds_rate].topk(K)[1]`` then ``i * ds_rate``
+  (gen_sample.py:87-88) evaluated verbatim with CPU torch (the module itself cannot be
+  imported: h5py / tensorboardX are absent);
+* HF ``GitVisionModel`` / ``CLIPImageProcessor`` (the third-party code the reference calls)
+  with the repo's seeded random ViT-B/16 weights.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import mdf, ref_loader, vit  # noqa: E402
+import sasvqa_b200.synth as synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class StubEncoder:
+    """Returns precomputed pooled rows; frames carry their own index in element 0."""
+
+    def __init__(self, raw):
+        self.raw = raw
+
+    def __call__(self, frames):
+        idx = frames.reshape(frames.shape[0], -1)[:, 0].long()
+        return SimpleNamespace(pooler_output=self.raw[idx])
+
+
+def structured_feats(rng: np.random.RandomState, T: int, D: int, kind: int) -> np.ndarray:
+    if kind == 0:      # iid
+        return rng.randn(T, D).astype(np.float32)
+    if kind == 1:      # random walk (smooth drift)
+        return np.cumsum(rng.randn(T, D).astype(np.float32) * 0.3, axis=0) + rng.randn(1, D).astype(np.float32)
+    # scenes + noise
+    n_sc = max(2, T // 16)
+    centers = rng.randn(n_sc, D).astype(np.float32)
+    cuts = np.sort(rng.choice(np.arange(1, max(T, 2)), size=min(n_sc - 1, max(T - 1, 1)), replace=False)) if T > 1 else []
+    sc = np.searchsorted(cuts, np.arange(T), side="right") if T > 1 else np.zeros(T, int)
+    return (centers[sc] + 0.25 * rng.randn(T, D)).astype(np.float32)
+
+
+def gen_mdf_select():
+    ref_mdf, _ = ref_loader.load_sampler_fns()
+    rng = np.random.RandomState(666)
+    D = 8
+    Ts = [0, 1, 2, 5, 15, 16, 17, 20, 21, 33, 40, 64, 100, 128, 129, 200, 257, 300, 512, 600]
+    cases = []
+    for T in Ts:
+        for K, W in [(16, 8), (8, 8), (8, 4), (4, 2), (32, 8), (16, -1), (1, 8), (3, 1), (16, 16), (5, 0), (32, 3)]:
+            cases.append((T, K, W, len(cases) % 3))
+    feats_all, meta, idx_all = [], [], []
+    for (T, K, W, kind) in cases:
+        raw = torch.from_numpy(structured_feats(rng, T, D, kind)) if T > 0 else torch.zeros(0, D)
+        frames = torch.arange(T, dtype=torch.float32).view(T, 1, 1, 1)
+        dc = {"Failure": 0, "Zeros": 0}
+        err = 0
+        try:
+            out = ref_mdf(frames, StubEncoder(raw), K, W, dc)
+            idx = [] if dc["Zeros"] else [int(v) for v in out.reshape(out.shape[0], -1)[:, 0].tolist()]
+            if dc["Zeros"]:
+                assert tuple(out.shape) == (K, 3, 224, 224) and float(out.abs().sum()) == 0.0
+        except RuntimeError:
+            err, idx = 1, []
+        meta.append([T, K, W, dc["Failure"], dc["Zeros"], err, len(idx)])
+        feats_all.append(raw.numpy().reshape(-1))
+        idx_all.append(np.asarray(idx, dtype=np.int64))
+    np.savez_compressed(
+        os.path.join(GOLD, "mdf_select.npz"),
+        meta=np.asarray(meta, dtype=np.int64), D=np.int64(D),
+        feats=np.concatenate(feats_all).astype(np.float32),
+        indices=np.concatenate(idx_all) if idx_all else np.zeros(0, np.int64))
+    print("mdf_select:", len(cases), "cases; fallback", sum(m[3] for m in meta), "errors", sum(m[5] for m in meta))
+
+
+def gen_misc():
+    _, ref_uniform = ref_loader.load_sampler_fns()
+    ref_git6 = ref_loader.load_sample_frame_indices()
+    uni_meta, uni_idx = [], []
+    for T in [8, 9, 16, 17, 31, 64, 100, 128, 300, 512, 1000]:
+        for K in [1, 3, 6, 8, 16, 32]:
+            if K > T:
+                continue
+            frames = torch.arange(T, dtype=torch.float32).view(T, 1)
+            out = ref_uniform(frames, K=K)
+            uni_meta.append([T, K])
+            uni_idx.append(out.reshape(-1).long().numpy())
+    git_meta, git_idx = [], []
+    np.random.seed(666)      # extract_features.py:140
+    for T in [33, 64, 65, 100, 128, 300, 512]:
+        for K in [6, 8, 16]:
+            if T <= 4 * K:
+                continue
+            frames = torch.arange(T, dtype=torch.float32)
+            out = ref_git6(frames, K, 4, T)
+            git_meta.append([T, K])
+            git_idx.append(out.long().numpy())
+    rng = np.random.RandomState(667)
+    mif_meta, mif_scores, mif_idx = [], [], []
+    for T in [8, 16, 17, 64, 128, 512]:
+        for K, ds_rate in [(8, 1), (8, 2), (4, 1), (6, 2), (3, 3), (16, 1)]:
+            if K > len(range(0, T, ds_rate)):
+                continue
+            s = torch.from_numpy(rng.randn(T).astype(np.float32))
+            inds = s[::ds_rate].topk(K)[1].detach().cpu().tolist()     # gen_sample.py:87
+            inds = [i * ds_rate for i in inds]                         # gen_sample.py:88
+            mif_meta.append([T, K, ds_rate])
+            mif_scores.append(s.numpy())
+            mif_idx.append(np.asarray(inds, dtype=np.int64))
+    np.savez_compressed(
+        os.path.join(GOLD, "samplers_misc.npz"),
+        uni_meta=np.asarray(uni_meta), uni_idx=np.concatenate(uni_idx),
+        git_meta=np.asarray(git_meta), git_idx=np.concatenate(git_idx),
+        mif_meta=np.asarray(mif_meta), mif_scores=np.concatenate(mif_scores), mif_idx=np.concatenate(mif_idx))
+    print("misc: uniform", len(uni_meta), "git6", len(git_meta), "mif", len(mif_meta))
+
+
+def recover_indices(frames, out):
+    flat = frames.reshape(frames.shape[0], -1)
+    res = []
+    for k in range(out.shape[0]):
+        hit = (flat == out[k].reshape(1, -1)).all(dim=1).nonzero().reshape(-1)
+        assert hit.numel() == 1
+        res.append(int(hit[0]))
+    return res
+
+
+def gen_encoder_and_e2e():
+    from transformers import CLIPImageProcessor
+    sd = synth.random_encoder_state_dict(synth.REF_SEED)
+    hf = vit.hf_model_from_state_dict(sd)
+    # --- image processor + encoder features on 4 frames
+    u8 = synth.make_clip(0, 4)
+    proc = CLIPImageProcessor()
+    px_hf = torch.from_numpy(np.stack(proc(images=[f.numpy() for f in u8])["pixel_values"]))
+    px = vit.image_processor_224(u8)
+    print("image processor max |diff| vs restatement:", float((px_hf - px).abs().max()))
+    with torch.no_grad():
+        hid = hf(px_hf).last_hidden_state
+    feats = torch.nn.functional.normalize(hid.mean(dim=1))
+    np.savez_compressed(
+        os.path.join(GOLD, "encoder_hf.npz"),
+        seed=np.int64(synth.REF_SEED), clip_id=np.int64(0), T=np.int64(4),
+        pixel_probe=px_hf[:, :, ::37, ::41].numpy(), pixel_sum=px_hf.double().sum(dim=(1, 2, 3)).numpy(),
+        hidden_probe=hid[:, ::49, ::64].numpy(), feats=feats.numpy())
+    # --- end-to-end MDF through the reference function + HF encoder
+    ref_mdf, _ = ref_loader.load_sampler_fns()
+    out = {}
+    for tag, (cid, T, K, W) in {"c1": (1, 64, 16, 8), "t64k8w4": (1, 64, 8, 4), "t128k8w8": (2, 128, 8, 8)}.items():
+        frames = vit.image_processor_224(synth.make_clip(cid, T))
+        dc = {"Failure": 0, "Zeros": 0}
+        t0 = time.time()
+        with torch.no_grad():
+            sel = ref_mdf(frames, hf, K, W, dc)
+        dt = time.time() - t0
+        idx = recover_indices(frames, sel)
+        with torch.no_grad():
+            _, aux = mdf.sample_representative_frames(frames, hf, K, W, {"Failure": 0, "Zeros": 0}, return_aux=True)
+        assert aux["indices"] == idx or all(
+            float(aux["lcl_avg"][a]) == float(aux["lcl_avg"][b]) for a, b in zip(aux["indices"], idx)), (aux["indices"], idx)
+        out[tag + "_meta"] = np.asarray([cid, T, K, W, dc["Failure"]], dtype=np.int64)
+        out[tag + "_indices"] = np.asarray(idx, dtype=np.int64)
+        out[tag + "_lcl"] = aux["lcl_avg"].numpy()
+        out[tag + "_feats"] = aux["feats"].numpy()
+        print(f"e2e {tag}: T={T} K={K} W={W} failure={dc['Failure']} idx={idx} ({dt:.1f}s)")
+    np.savez_compressed(os.path.join(GOLD, "mdf_e2e_hf.npz"), **out)
+
+
+if __name__ == "__main__":
+    assert ref_loader.available(), "needs /root/reference"
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    gen_mdf_select()
+    gen_misc()
+    gen_encoder_and_e2e()

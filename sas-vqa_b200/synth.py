@@ -1,0 +1,135 @@
+"""Synthetic inputs for the frame-sampling hot path (no datasets or checkpoints offline).
+
+Clips follow SURVEY.md section 8(d): scene-structured uint8 RGB clips laid out
+``[T, H, W, 3]`` (HWC, what cv2 delivers after the BGR->RGB swap in the reference,
+``src/preprocessing/prefetch_loader.py:57-67``), seeded ``666 + clip_id`` (666 is the
+reference's seed, ``src/preprocessing/extract_features.py:136``).
+
+Encoder weights are a seeded random ViT-B/16 state dict using the key names of the HF
+``GitVisionModel`` the reference loads (``extract_features.py:145``), so the same dict
+feeds the CUDA encoder, the oracle restatement and HF itself.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+IMG = 224
+PATCH = 16
+HIDDEN = 768
+HEADS = 12
+FFN = 3072
+LAYERS = 12
+TOKENS = (IMG // PATCH) ** 2 + 1  # 197
+REF_SEED = 666
+
+# CLIPImageProcessor defaults (the reference's AutoProcessor)
+IMAGE_MEAN = (0.48145466, 0.4578275, 0.40821073)
+IMAGE_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def make_clip(clip_id: int, T: int, device="cpu", seed: int = REF_SEED, H: int = IMG, W: int = IMG,
+              structured: bool = True) -> torch.Tensor:
+    """One uint8 clip ``[T, H, W, 3]``.
+
+    structured=True: ``max(2, T // 16)`` low-frequency scenes (7x7 noise, bicubic upsample),
+    contiguous scene segments of random length, a slow per-frame gain drift and N(0, 0.05)
+    pixel noise.  structured=False: iid uniform noise (throughput only).
+    """
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + int(clip_id))
+    if T == 0:
+        return torch.zeros(0, H, W, 3, dtype=torch.uint8, device=dev)
+    if not structured:
+        return torch.randint(0, 256, (T, H, W, 3), generator=g, device=dev, dtype=torch.uint8)
+    n_scenes = max(2, T // 16)
+    low = torch.rand(n_scenes, 3, 7, 7, generator=g, device=dev)
+    scenes = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False)
+    scenes = scenes.clamp_(0.0, 1.0)
+    # contiguous segments with random cut points
+    w = torch.rand(n_scenes, generator=g, device=dev) + 0.25
+    bounds = torch.cumsum(w / w.sum(), 0) * T
+    t = torch.arange(T, device=dev, dtype=torch.float32)
+    scene_of_t = torch.bucketize(t + 0.5, bounds[:-1].contiguous())
+    phase = torch.rand(2, generator=g, device=dev)
+    gain = 1.0 + 0.12 * torch.sin(2 * math.pi * (t / max(T, 1) * (1.0 + 2.0 * phase[0]) + phase[1]))
+    out = torch.empty(T, H, W, 3, dtype=torch.uint8, device=dev)
+    step = 64
+    for s in range(0, T, step):
+        e = min(T, s + step)
+        fr = scenes[scene_of_t[s:e]] * gain[s:e, None, None, None]
+        fr = fr + 0.05 * torch.randn(e - s, 3, H, W, generator=g, device=dev)
+        out[s:e] = (fr.clamp_(0.0, 1.0) * 255.0).round_().to(torch.uint8).permute(0, 2, 3, 1)
+    return out
+
+
+def make_clips(clip_ids, T: int, device="cpu", seed: int = REF_SEED, structured: bool = True) -> torch.Tensor:
+    """Batch of clips ``[B, T, H, W, 3]`` uint8."""
+    ids = list(clip_ids)
+    out = torch.empty(len(ids), T, IMG, IMG, 3, dtype=torch.uint8, device=device)
+    for b, cid in enumerate(ids):
+        out[b] = make_clip(cid, T, device=device, seed=seed, structured=structured)
+    return out
+
+
+def normalize_frames_reference(u8_hwc: torch.Tensor) -> torch.Tensor:
+    """fp32 ``[T, 3, H, W]`` exactly as the HF image processor produces for 224x224 input
+    (resize and centre-crop are identities there): ``(x * (1/255) - mean) / std``.
+    Host/torch helper for tests and the reference arm; the product path does this in K1/K5."""
+    x = u8_hwc.permute(0, 3, 1, 2).to(torch.float32) * (1.0 / 255.0)
+    mean = torch.tensor(IMAGE_MEAN, dtype=torch.float32, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGE_STD, dtype=torch.float32, device=x.device).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+def state_dict_keys():
+    keys = [
+        ("vision_model.embeddings.class_embedding", (HIDDEN,)),
+        ("vision_model.embeddings.patch_embedding.weight", (HIDDEN, 3, PATCH, PATCH)),
+        ("vision_model.embeddings.position_embedding.weight", (TOKENS, HIDDEN)),
+        ("vision_model.pre_layrnorm.weight", (HIDDEN,)),
+        ("vision_model.pre_layrnorm.bias", (HIDDEN,)),
+    ]
+    for l in range(LAYERS):
+        p = f"vision_model.encoder.layers.{l}."
+        for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            keys.append((p + f"self_attn.{nm}.weight", (HIDDEN, HIDDEN)))
+            keys.append((p + f"self_attn.{nm}.bias", (HIDDEN,)))
+        keys.append((p + "layer_norm1.weight", (HIDDEN,)))
+        keys.append((p + "layer_norm1.bias", (HIDDEN,)))
+        keys.append((p + "mlp.fc1.weight", (FFN, HIDDEN)))
+        keys.append((p + "mlp.fc1.bias", (FFN,)))
+        keys.append((p + "mlp.fc2.weight", (HIDDEN, FFN)))
+        keys.append((p + "mlp.fc2.bias", (HIDDEN,)))
+        keys.append((p + "layer_norm2.weight", (HIDDEN,)))
+        keys.append((p + "layer_norm2.bias", (HIDDEN,)))
+    keys.append(("vision_model.post_layernorm.weight", (HIDDEN,)))
+    keys.append(("vision_model.post_layernorm.bias", (HIDDEN,)))
+    return keys
+
+
+def random_encoder_state_dict(seed: int = REF_SEED, bf16_exact: bool = True) -> dict:
+    """Seeded random ViT-B/16 weights under HF ``GitVisionModel`` key names (fp32, CPU).
+
+    Unlike HF's default init, LayerNorm gains/biases and linear biases are non-trivial so
+    every term of the encoder is exercised.  With ``bf16_exact`` the matrices that the CUDA
+    path stores in bf16 are rounded to bf16-representable fp32 values, so the fp32 reference
+    and the bf16 kernels see identical weights and differ only by activation rounding.
+    """
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sd = {}
+    for name, shape in state_dict_keys():
+        if name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") \
+                or name.endswith("layrnorm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g)
+        if bf16_exact and t.dim() >= 2 and "position_embedding" not in name:
+            t = t.to(torch.bfloat16).to(torch.float32)
+        sd[name] = t.contiguous()
+    return sd

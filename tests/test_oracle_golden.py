@@ -1,0 +1,176 @@
+"""Pins the CPU oracle: against the fixtures produced by the reference itself
+(oracle/make_golden.py) and, when /root/reference is present, against the live reference."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mdf, ref_loader, vit
+import sasvqa_b200.synth as synth
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _iter_mdf_cases(g):
+    D = int(g["D"])
+    fo = io = 0
+    for T, K, W, failure, zeros, err, n_idx in g["meta"].tolist():
+        feats = g["feats"][fo:fo + T * D].reshape(T, D)
+        idx = g["indices"][io:io + n_idx].tolist()
+        fo += T * D
+        io += n_idx
+        yield T, K, W, failure, zeros, err, feats, idx
+
+
+def assert_same_or_tied(got, want, scores):
+    """Index lists must match position by position except where both picks carry EXACTLY
+    the same score (torch.topk's order among equal values is implementation-defined)."""
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        if a != b:
+            assert float(scores[a]) == float(scores[b]), (got, want)
+
+
+def test_mdf_select_matches_reference_fixtures(golden_dir):
+    g = _load(golden_dir, "mdf_select.npz")
+    n = n_fb = n_err = 0
+    for T, K, W, failure, zeros, err, feats, want in _iter_mdf_cases(g):
+        n += 1
+        if T == 0:
+            assert zeros == 1
+            continue
+        f = torch.nn.functional.normalize(torch.from_numpy(feats.copy()))
+        if err:
+            n_err += 1
+            with pytest.raises(RuntimeError):
+                mdf.mdf_indices_from_feats(f, K, W)
+            continue
+        idx, status, lcl, _ = mdf.mdf_indices_from_feats(f, K, W)
+        assert status == (mdf.STATUS_FALLBACK if failure else mdf.STATUS_OK)
+        n_fb += failure
+        assert_same_or_tied(idx, want, lcl)
+    assert n >= 100 and n_fb > 10 and n_err > 5
+
+
+def test_mdf_select_exact_where_no_ties(golden_dir):
+    """On cases whose interior scores are all distinct and whose picks avoid the zero
+    borders the oracle must be identical to the reference with no excuses."""
+    g = _load(golden_dir, "mdf_select.npz")
+    exact = 0
+    for T, K, W, failure, zeros, err, feats, want in _iter_mdf_cases(g):
+        if T == 0 or err:
+            continue
+        f = torch.nn.functional.normalize(torch.from_numpy(feats.copy()))
+        idx, status, lcl, _ = mdf.mdf_indices_from_feats(f, K, W)
+        vals = lcl.numpy()
+        if len(np.unique(vals[want])) == len(want) and np.all(vals[want] != 0):
+            assert idx == want
+            exact += 1
+    assert exact >= 40
+
+
+def test_uniform_git6_mif_fixtures(golden_dir):
+    g = _load(golden_dir, "samplers_misc.npz")
+    o = 0
+    for T, K in g["uni_meta"].tolist():
+        assert mdf.uniform_indices(T, K) == g["uni_idx"][o:o + K].tolist()
+        o += K
+    o = 0
+    rng = np.random.RandomState(666)
+    for T, K in g["git_meta"].tolist():
+        got = mdf.git6_indices(T, K, 4, rng=rng)
+        assert got.tolist() == g["git_idx"][o:o + K].tolist()
+        o += K
+    o = so = 0
+    for T, K, ds in g["mif_meta"].tolist():
+        s = g["mif_scores"][so:so + T]
+        assert mdf.mif_select(s, K, ds) == g["mif_idx"][o:o + K].tolist()
+        o += K
+        so += T
+
+
+def test_known_answer_edges():
+    # T <= 2W: all-zero scores, argmax 0
+    lcl = mdf.local_average(torch.eye(10), 8)
+    assert float(lcl.abs().sum()) == 0.0
+    # W = -1 with T < 20 -> W = 0 -> every score (0 - 1) / (0 - 1) = 1
+    f = torch.nn.functional.normalize(torch.randn(12, 8))
+    idx, status, lcl, _ = mdf.mdf_indices_from_feats(f, 4, -1)
+    assert torch.all(lcl == 1.0)
+    # two equal-height peaks: heap tie falls to the smaller left edge
+    lcl = torch.zeros(64)
+    lcl[30] = 0.9
+    lcl[10] = 0.5
+    lcl[50] = 0.5
+    assert mdf.greedy_select(lcl, 3, 4) == [30, 10, 50]
+    # spacing: picks differ by >= W
+    lcl = torch.rand(200)
+    picks = mdf.greedy_select(lcl, 10, 8)
+    assert len(picks) == 10 and min(abs(a - b) for i, a in enumerate(picks) for b in picks[:i]) >= 8
+    # fallback with T < K raises like torch.topk
+    with pytest.raises(RuntimeError):
+        mdf.mdf_select(torch.zeros(4), 8, 8)
+
+
+def test_encoder_restatement_matches_hf_fixture(golden_dir):
+    g = _load(golden_dir, "encoder_hf.npz")
+    sd = synth.random_encoder_state_dict(int(g["seed"]))
+    u8 = synth.make_clip(int(g["clip_id"]), int(g["T"]))
+    px = vit.image_processor_224(u8)
+    assert np.abs(px[:, :, ::37, ::41].numpy() - g["pixel_probe"]).max() < 1e-6
+    assert np.abs(px.double().sum(dim=(1, 2, 3)).numpy() - g["pixel_sum"]).max() < 1e-1
+    enc = vit.VitOracle(sd)
+    hid = enc.forward_hidden(px)
+    assert np.abs(hid[:, ::49, ::64].numpy() - g["hidden_probe"]).max() < 2e-4
+    feats = torch.nn.functional.normalize(hid.mean(dim=1)).numpy()
+    assert np.abs(feats - g["feats"]).max() < 1e-5
+
+
+def test_e2e_fixture_selection_from_reference_features(golden_dir):
+    g = _load(golden_dir, "mdf_e2e_hf.npz")
+    for tag in ("c1", "t64k8w4", "t128k8w8"):
+        cid, T, K, W, failure = g[tag + "_meta"].tolist()
+        feats = torch.from_numpy(g[tag + "_feats"])
+        idx, status, lcl, _ = mdf.mdf_indices_from_feats(feats, K, W)
+        assert status == failure
+        assert np.abs(lcl.numpy() - g[tag + "_lcl"]).max() < 1e-6
+        assert idx == g[tag + "_indices"].tolist()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference absent (GPU box)")
+def test_live_reference_agrees_on_fresh_random_cases():
+    ref_mdf, ref_uni = ref_loader.load_sampler_fns()
+    rng = np.random.RandomState(4242)
+    checked = 0
+    for trial in range(120):
+        T = int(rng.choice([7, 24, 50, 64, 96, 128, 200, 333]))
+        K = int(rng.choice([2, 4, 8, 16]))
+        W = int(rng.choice([-1, 1, 2, 4, 8]))
+        raw = torch.from_numpy(np.cumsum(rng.randn(T, 6).astype(np.float32), axis=0))
+
+        class Stub:
+            def __call__(self, frames):
+                i = frames.reshape(frames.shape[0], -1)[:, 0].long()
+                return SimpleNamespace(pooler_output=raw[i])
+
+        frames = torch.arange(T, dtype=torch.float32).view(T, 1, 1, 1)
+        dc = {"Failure": 0, "Zeros": 0}
+        try:
+            want = ref_mdf(frames, Stub(), K, W, dc).reshape(-1).long().tolist()
+        except RuntimeError:
+            with pytest.raises(RuntimeError):
+                mdf.sample_representative_frames(frames, Stub(), K, W, {"Failure": 0, "Zeros": 0})
+            continue
+        dc2 = {"Failure": 0, "Zeros": 0}
+        out, aux = mdf.sample_representative_frames(frames, Stub(), K, W, dc2, return_aux=True)
+        assert dc2 == dc
+        assert_same_or_tied(aux["indices"], want, aux["lcl_avg"])
+        assert out.reshape(-1).long().tolist() == aux["indices"]
+        checked += 1
+    assert checked >= 80
+    frames = torch.arange(100, dtype=torch.float32).view(100, 1)
+    assert ref_uni(frames, K=8).reshape(-1).long().tolist() == mdf.uniform_indices(100, 8)
