@@ -1,0 +1,137 @@
+/* sasvqa.h -- C ABI of libsasvqa_b200.so: the B200-native frame-sampling hot path of SAS-VQA.
+ *
+ * The reference (Clement25/SAS-VQA) has no FFI: its seam is the Python call
+ *     exted_frms = sample_representative_frames(video_frms, model, args.K, args.W, debug_counter)
+ * (src/preprocessing/extract_features.py:90 -> src/preprocessing/datautils/utils.py:31-94) and
+ * its MIF sibling  inds = scores[::ds_rate].topk(args.K)[1]  (src/preprocessing/gen_sample.py:87-88).
+ * These entry points are what a ctypes binding of that seam calls (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every function returns 0 (SASVQA_OK) or an error code and never throws;
+ * sasvqa_last_error() returns the message of the calling thread's last failure.  Pointers named
+ * *_dev are CUDA device pointers on the current device, *_host are host pointers (pinned memory
+ * makes the copies asynchronous).  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream); device-pointer entry points are asynchronous on it, host-pointer entry points return
+ * after the results are in host memory.  Outputs are caller-allocated.  bf16 buffers are passed
+ * as uint16_t*.  Frames are 224x224 (ViT-B/16 input of the reference's GitVisionModel).
+ */
+#ifndef SASVQA_H
+#define SASVQA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SASVQA_OK 0
+#define SASVQA_ERR_INVALID 1     /* bad argument / unsupported shape */
+#define SASVQA_ERR_CUDA 2        /* a CUDA call failed */
+#define SASVQA_ERR_NOMEM 3
+
+/* per-clip status written by the selection stage */
+#define SASVQA_STATUS_OK 0         /* K picks from the greedy spacing rule            (utils.py:63-88) */
+#define SASVQA_STATUS_FALLBACK 1   /* fewer than K: plain top-K taken, 'Failure' += 1 (utils.py:91-93) */
+#define SASVQA_STATUS_EMPTY 2      /* T == 0: zero frames returned, 'Zeros' += 1      (utils.py:50-52) */
+#define SASVQA_STATUS_TOO_FEW 3    /* fallback with T < K: the reference raises RuntimeError here      */
+
+#define SASVQA_NUM_ENCODER_PARAMS 85799424ull /* fp32 values in a GitVisionModel ViT-B/16 state dict */
+
+typedef struct SasvqaEncoder SasvqaEncoder; /* frozen frame encoder: bf16 weights + workspace on one GPU */
+
+int sasvqa_abi_version(void);
+const char* sasvqa_last_error(void);
+
+/* ---- encoder handle ------------------------------------------------------------------------
+ * Replaces `GitVisionModel.from_pretrained(...)` + `.eval().cuda()` (extract_features.py:145,45-47).
+ * params_host: the model's state_dict flattened to fp32 in HF key order: class_embedding,
+ * patch_embedding.weight, position_embedding.weight, pre_layrnorm.{weight,bias}, then per layer
+ * {k,v,q,out}_proj.{weight,bias}, layer_norm1.{weight,bias}, mlp.fc1.{weight,bias},
+ * mlp.fc2.{weight,bias}, layer_norm2.{weight,bias}, then post_layernorm.{weight,bias}.
+ * chunk_frames: frames encoded per pass (workspace ~2.1 MB per frame); <= 0 picks the default. */
+int sasvqa_encoder_create(const float* params_host, uint64_t n_params, int chunk_frames, SasvqaEncoder** out);
+void sasvqa_encoder_destroy(SasvqaEncoder* enc);
+int sasvqa_encoder_chunk_frames(const SasvqaEncoder* enc);
+
+/* ---- K1: preprocessing ---------------------------------------------------------------------
+ * uint8 HWC frames -> (x/255 - mean)/std -> bf16 patch matrix [n*196, 768], column = c*256+iy*16+ix.
+ * Replaces the host image processor (prefetch_loader.py:74-75; 224x224 input) + the conv's im2col. */
+int sasvqa_preprocess_u8(const uint8_t* frames_hwc_dev, int n_frames, uint16_t* patches_bf16_dev, void* stream);
+/* same layout from already normalised fp32 CHW frames (the type utils.py:31 receives) */
+int sasvqa_patchify_f32(const float* frames_chw_dev, int n_frames, uint16_t* patches_bf16_dev, void* stream);
+
+/* ---- K2 + K3a: encoder forward + pooling -----------------------------------------------------
+ * patches -> ViT-B/16 -> post-LN -> mean over 197 tokens -> L2 normalise: feats [n, 768] fp32 unit rows.
+ * Replaces utils.py:39-48 (model(chunk), .last_hidden_state.mean(1), normalize). */
+int sasvqa_encoder_fwd(SasvqaEncoder* enc, const uint16_t* patches_bf16_dev, int n_frames, float* feats_dev,
+                       void* stream);
+/* inspection: fp32 hidden state [n, 197, 768] after `n_layers` blocks (before post_layernorm); n <= chunk */
+int sasvqa_encoder_fwd_hidden(SasvqaEncoder* enc, const uint16_t* patches_bf16_dev, int n_frames, int n_layers,
+                              float* hidden_dev, void* stream);
+
+/* ---- K3b + K4a: windowed mean cosine similarity (utils.py:55-61) -----------------------------
+ * feats [B, T, 768] -> lcl_avg [B, T]; W >= 0 (resolve W == -1 to T / 20 first, utils.py:32-33).
+ * gram_or_null: optional [B, T, T] full Gram matrix (the reference materialises it; we only need the band). */
+int sasvqa_mdf_scores(const float* feats_dev, int B, int T, int W, float* lcl_avg_dev, float* gram_or_null_dev,
+                      void* stream);
+
+/* ---- K4b: greedy selection + top-K fallback (utils.py:63-93) ---------------------------------
+ * lcl_avg [B, T] -> idx [B, K] int32 in importance order, status [B] (SASVQA_STATUS_*). */
+int sasvqa_mdf_select(const float* lcl_avg_dev, int B, int T, int K, int W, int32_t* idx_dev, int32_t* status_dev,
+                      void* stream);
+
+/* ---- K4c: MIF strided top-K (gen_sample.py:87-88) --------------------------------------------
+ * idx[b, :] = ds_rate * topk(scores[b, ::ds_rate], K), best first. */
+int sasvqa_topk_strided(const float* scores_dev, int B, int T, int ds_rate, int K, int32_t* idx_dev, void* stream);
+
+/* ---- K5: gather the selected frames as normalised fp32 rows (utils.py:94, extract_features.py:96)
+ * out [B, K, 3*224*224]; out-of-range indices give zero rows. */
+int sasvqa_gather_frames_u8(const uint8_t* clips_hwc_dev, const int32_t* idx_dev, int B, int T, int K,
+                            float* out_dev, void* stream);
+int sasvqa_gather_frames_f32(const float* frames_dev, const int32_t* idx_dev, int B, int T, int K,
+                             int64_t row_elems, float* out_dev, void* stream);
+
+/* ---- whole path, device-resident clips ------------------------------------------------------
+ * clips [B, T, 224, 224, 3] uint8 -> idx [B, K], status [B]; optional outputs may be NULL:
+ * lcl_avg [B, T], feats [B, T, 768], sampled [B, K, 3*224*224] fp32.  W may be -1 (adaptive). */
+int sasvqa_mdf_sample_u8(SasvqaEncoder* enc, const uint8_t* clips_hwc_dev, int B, int T, int K, int W,
+                         int32_t* idx_dev, int32_t* status_dev, float* lcl_avg_or_null_dev,
+                         float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
+/* same from normalised fp32 CHW frames [B, T, 3, 224, 224] (the reference sampler's input) */
+int sasvqa_mdf_sample_f32(SasvqaEncoder* enc, const float* clips_chw_dev, int B, int T, int K, int W,
+                          int32_t* idx_dev, int32_t* status_dev, float* lcl_avg_or_null_dev,
+                          float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
+
+/* ---- whole path, HOST buffers (the extraction loop extract_features.py:80-97 for a clip list) --
+ * Streams clips host->device in double-buffered groups overlapped with compute, writes idx/status
+ * (and, if not NULL, the sampled frames -- the rows of the reference's "sampled_frames" dataset)
+ * back to host memory.  Returns after everything is on the host. */
+int sasvqa_mdf_sample_host(SasvqaEncoder* enc, const uint8_t* clips_hwc_host, int B, int T, int K, int W,
+                           int32_t* idx_host, int32_t* status_host, float* sampled_or_null_host);
+
+/* ---- instrumentation ------------------------------------------------------------------------
+ * sasvqa_launch_count: kernels launched by this library in this process so far.
+ * Profiling: when enabled, CUDA-event pairs bracket every stage launch on its stream;
+ * sasvqa_profile_read synchronises, sums milliseconds and scope counts per stage kind and resets.
+ * Kinds: 0 preprocess, 1 gemm_patch_embed, 2 pre_layernorm, 3 layernorm, 4 gemm_qkv, 5 attention,
+ * 6 gemm_out_proj, 7 gemm_fc1, 8 gemm_fc2, 9 pool_norm, 10 scores, 11 select, 12 gather. */
+#define SASVQA_PROFILE_KINDS 13
+int64_t sasvqa_launch_count(void);
+int sasvqa_profile_enable(SasvqaEncoder* enc, int on);
+int sasvqa_profile_read(SasvqaEncoder* enc, double* ms_out, int64_t* scopes_out, int n_kinds);
+
+/* ---- test hooks (not on the product path) ---------------------------------------------------
+ * One encoder GEMM with a fused epilogue (mode = 0 bias->bf16, 1 bias+quick_gelu->bf16,
+ * 2 bias+residual in place fp32, 3 patch-embed scatter + position embedding).  use_simt != 0 runs
+ * the CUDA-core check kernel instead of the tcgen05 kernel. */
+int sasvqa_test_gemm(const uint16_t* a_bf16_dev, const uint16_t* b_bf16_dev, int M, int N, int K, int mode,
+                     const float* bias_or_pos_dev, uint16_t* out_bf16_dev, float* out_f32_dev, int use_simt,
+                     void* stream);
+int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* out_bf16_dev, void* stream);
+int sasvqa_test_layernorm(const float* x_dev, int rows, const float* gamma_dev, const float* beta_dev,
+                          uint16_t* out_bf16_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SASVQA_H */

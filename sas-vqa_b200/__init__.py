@@ -1,2 +1,23 @@
-"""sasvqa_b200 -- B200-native SAS-VQA frame-sampling hot path."""
+"""sasvqa_b200 -- B200-native SAS-VQA frame-sampling hot path.
+
+The package directory is ``sas-vqa_b200/``; import it as ``sasvqa_b200`` (alias shim at the
+repo root).  The compute lives in ``libsasvqa_b200.so`` (hand-written sm_100a CUDA, C ABI in
+``include/sasvqa.h``); this Python layer mirrors the reference's sampler interface and raises
+if the library is missing -- there is no CPU fallback.
+"""
 from . import synth  # noqa: F401
+from ._capi import LIB_PATH, SasvqaError  # noqa: F401
+from .ops import FrameEncoder, STATUS_EMPTY, STATUS_FALLBACK, STATUS_OK, STATUS_TOO_FEW  # noqa: F401
+from .sampler import (  # noqa: F401
+    mif_select,
+    sample_frame_indices,
+    sample_frames_uniform,
+    sample_mdf_batch,
+    sample_mdf_host,
+    sample_representative_frames,
+)
+
+__all__ = [
+    "FrameEncoder", "SasvqaError", "mif_select", "sample_frame_indices", "sample_frames_uniform",
+    "sample_mdf_batch", "sample_mdf_host", "sample_representative_frames", "synth",
+]

@@ -1,0 +1,83 @@
+"""ctypes binding of libsasvqa_b200.so (C ABI in include/sasvqa.h).
+
+There is no CPU fallback: if the library is missing or a call fails this raises.  PyTorch is
+used only for device memory and streams; every signature below is plain pointers and sizes.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint16, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsasvqa_b200.so")
+
+_p = c_void_p  # device / host pointers are passed as raw addresses
+
+SIGNATURES = {
+    "sasvqa_abi_version": (c_int, []),
+    "sasvqa_last_error": (c_char_p, []),
+    "sasvqa_encoder_create": (c_int, [_p, c_uint64, c_int, POINTER(c_void_p)]),
+    "sasvqa_encoder_destroy": (None, [_p]),
+    "sasvqa_encoder_chunk_frames": (c_int, [_p]),
+    "sasvqa_preprocess_u8": (c_int, [_p, c_int, _p, _p]),
+    "sasvqa_patchify_f32": (c_int, [_p, c_int, _p, _p]),
+    "sasvqa_encoder_fwd": (c_int, [_p, _p, c_int, _p, _p]),
+    "sasvqa_encoder_fwd_hidden": (c_int, [_p, _p, c_int, c_int, _p, _p]),
+    "sasvqa_mdf_scores": (c_int, [_p, c_int, c_int, c_int, _p, _p, _p]),
+    "sasvqa_mdf_select": (c_int, [_p, c_int, c_int, c_int, c_int, _p, _p, _p]),
+    "sasvqa_topk_strided": (c_int, [_p, c_int, c_int, c_int, c_int, _p, _p]),
+    "sasvqa_gather_frames_u8": (c_int, [_p, _p, c_int, c_int, c_int, _p, _p]),
+    "sasvqa_gather_frames_f32": (c_int, [_p, _p, c_int, c_int, c_int, c_int64, _p, _p]),
+    "sasvqa_mdf_sample_u8": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
+    "sasvqa_mdf_sample_f32": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
+    "sasvqa_mdf_sample_host": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p]),
+    "sasvqa_launch_count": (c_int64, []),
+    "sasvqa_profile_enable": (c_int, [_p, c_int]),
+    "sasvqa_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
+    "sasvqa_test_gemm": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, c_int, _p]),
+    "sasvqa_test_attention": (c_int, [_p, c_int, _p, _p]),
+    "sasvqa_test_layernorm": (c_int, [_p, c_int, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class SasvqaError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the CUDA library; raises loudly when it has not been built (python -m sasvqa_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SasvqaError(
+                f"{LIB_PATH} is missing: the CUDA extension is not built and there is no CPU fallback. "
+                "Run `python __graft_entry__.py` (or sasvqa_b200.build.build()).")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().sasvqa_last_error()
+        raise SasvqaError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int | None:
+    """Raw address of a torch tensor (device or host) or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensor must be contiguous"
+    return t.data_ptr()
+
+
+def current_stream_ptr(device=None) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,130 @@
+// extern "C" surface of libsasvqa_b200.so (declared in include/sasvqa.h).
+#include <atomic>
+
+#include "../../include/sasvqa.h"
+#include "common.cuh"
+
+namespace sasvqa {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int profile_enable(SasvqaEncoder*, int);
+int profile_read(SasvqaEncoder*, double*, int64_t*, int);
+
+int encoder_create(const float*, uint64_t, int, SasvqaEncoder**);
+void encoder_destroy(SasvqaEncoder*);
+int encoder_chunk_frames(const SasvqaEncoder*);
+int encoder_fwd(SasvqaEncoder*, const __nv_bfloat16*, int, float*, cudaStream_t);
+int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, cudaStream_t);
+int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int32_t*, int32_t*, float*,
+                      float*, float*, cudaStream_t);
+int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int32_t*, int32_t*, float*);
+
+}  // namespace sasvqa
+
+using namespace sasvqa;
+
+#define S(stream) (reinterpret_cast<cudaStream_t>(stream))
+#define BF(p) (reinterpret_cast<__nv_bfloat16*>(p))
+#define CBF(p) (reinterpret_cast<const __nv_bfloat16*>(p))
+
+extern "C" {
+
+int sasvqa_abi_version(void) { return 1; }
+const char* sasvqa_last_error(void) { return g_last_error.c_str(); }
+int64_t sasvqa_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+int sasvqa_profile_enable(SasvqaEncoder* enc, int on) { return profile_enable(enc, on); }
+int sasvqa_profile_read(SasvqaEncoder* enc, double* ms, int64_t* launches, int n_kinds) {
+    return profile_read(enc, ms, launches, n_kinds);
+}
+
+int sasvqa_encoder_create(const float* params_host, uint64_t n_params, int chunk_frames, SasvqaEncoder** out) {
+    return encoder_create(params_host, n_params, chunk_frames, out);
+}
+void sasvqa_encoder_destroy(SasvqaEncoder* enc) { encoder_destroy(enc); }
+int sasvqa_encoder_chunk_frames(const SasvqaEncoder* enc) { return encoder_chunk_frames(enc); }
+
+int sasvqa_preprocess_u8(const uint8_t* frames, int n_frames, uint16_t* patches, void* stream) {
+    SASVQA_REQUIRE(n_frames >= 0 && (n_frames == 0 || (frames && patches)), "bad arguments");
+    return launch_preprocess_u8(frames, n_frames, BF(patches), S(stream));
+}
+int sasvqa_patchify_f32(const float* frames, int n_frames, uint16_t* patches, void* stream) {
+    SASVQA_REQUIRE(n_frames >= 0 && (n_frames == 0 || (frames && patches)), "bad arguments");
+    return launch_patchify_f32(frames, n_frames, BF(patches), S(stream));
+}
+
+int sasvqa_encoder_fwd(SasvqaEncoder* enc, const uint16_t* patches, int n_frames, float* feats, void* stream) {
+    return encoder_fwd(enc, CBF(patches), n_frames, feats, S(stream));
+}
+int sasvqa_encoder_fwd_hidden(SasvqaEncoder* enc, const uint16_t* patches, int n_frames, int n_layers, float* hidden,
+                              void* stream) {
+    return encoder_fwd_hidden(enc, CBF(patches), n_frames, n_layers, hidden, S(stream));
+}
+
+int sasvqa_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram_or_null, void* stream) {
+    SASVQA_REQUIRE(B >= 0 && T >= 0, "bad B/T");
+    SASVQA_REQUIRE(B == 0 || T == 0 || (feats && lcl_avg), "null argument");
+    return launch_mdf_scores(feats, B, T, W, lcl_avg, gram_or_null, S(stream));
+}
+int sasvqa_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status, void* stream) {
+    SASVQA_REQUIRE(B >= 0, "bad B");
+    SASVQA_REQUIRE(B == 0 || (lcl_avg && idx && status), "null argument");
+    return launch_mdf_select(lcl_avg, B, T, K, W, idx, status, S(stream));
+}
+int sasvqa_topk_strided(const float* scores, int B, int T, int ds_rate, int K, int32_t* idx, void* stream) {
+    SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 0, "bad B/T/K");
+    SASVQA_REQUIRE(B == 0 || K == 0 || (scores && idx), "null argument");
+    return launch_topk_strided(scores, B, T, ds_rate, K, idx, nullptr, S(stream));
+}
+
+int sasvqa_gather_frames_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, void* stream) {
+    SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 0, "bad B/T/K");
+    return launch_gather_u8(clips, idx, B, T, K, out, S(stream));
+}
+int sasvqa_gather_frames_f32(const float* frames, const int32_t* idx, int B, int T, int K, int64_t row_elems,
+                             float* out, void* stream) {
+    SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 0 && row_elems >= 0, "bad B/T/K/row_elems");
+    return launch_gather_f32(frames, idx, B, T, K, row_elems, out, S(stream));
+}
+
+int sasvqa_mdf_sample_u8(SasvqaEncoder* enc, const uint8_t* clips, int B, int T, int K, int W, int32_t* idx,
+                         int32_t* status, float* lcl_avg, float* feats, float* sampled, void* stream) {
+    SASVQA_REQUIRE(B == 0 || T == 0 || clips != nullptr, "null clips");
+    return mdf_sample_device(enc, clips, nullptr, B, T, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+}
+int sasvqa_mdf_sample_f32(SasvqaEncoder* enc, const float* clips, int B, int T, int K, int W, int32_t* idx,
+                          int32_t* status, float* lcl_avg, float* feats, float* sampled, void* stream) {
+    SASVQA_REQUIRE(B == 0 || T == 0 || clips != nullptr, "null clips");
+    return mdf_sample_device(enc, nullptr, clips, B, T, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+}
+int sasvqa_mdf_sample_host(SasvqaEncoder* enc, const uint8_t* clips_host, int B, int T, int K, int W, int32_t* idx_host,
+                           int32_t* status_host, float* sampled_host) {
+    return mdf_sample_host(enc, clips_host, B, T, K, W, idx_host, status_host, sampled_host);
+}
+
+int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, int mode, const float* bias_or_pos,
+                     uint16_t* out_bf16, float* out_f32, int use_simt, void* stream) {
+    SASVQA_REQUIRE(a && b && mode >= 0 && mode <= 3, "bad arguments");
+    GemmArgs g{};
+    g.A = CBF(a); g.B = CBF(b); g.M = M; g.N = N; g.K = K; g.epilogue = mode;
+    g.bias = bias_or_pos; g.pos = bias_or_pos; g.out_bf16 = BF(out_bf16); g.out_f32 = out_f32;
+    if (use_simt) return launch_gemm_simt(g, S(stream));
+    CUtensorMap ma, mb;
+    int rc = make_tensor_map_bf16_kmajor(&ma, a, (uint64_t)M, (uint64_t)K, 128);
+    if (rc) return rc;
+    if ((rc = make_tensor_map_bf16_kmajor(&mb, b, (uint64_t)N, (uint64_t)K, 256))) return rc;
+    int dev = 0, sms = 148;
+    SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
+    SASVQA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_gemm_tcgen05(g, &ma, &mb, sms, S(stream));
+}
+int sasvqa_test_attention(const uint16_t* qkv, int n_frames, uint16_t* out, void* stream) {
+    return launch_attention(CBF(qkv), BF(out), n_frames, S(stream));
+}
+int sasvqa_test_layernorm(const float* x, int rows, const float* gamma, const float* beta, uint16_t* out, void* stream) {
+    return launch_layernorm_bf16(x, BF(out), rows, gamma, beta, S(stream));
+}
+
+}  // extern "C"

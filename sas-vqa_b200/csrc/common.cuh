@@ -1,0 +1,123 @@
+// Shared device/host helpers for the sasvqa_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+namespace sasvqa {
+
+// ---- model constants: ViT-B/16 @224 (HF GitVisionConfig defaults; the reference's encoder,
+// src/preprocessing/extract_features.py:145)
+constexpr int kImg = 224;
+constexpr int kPatch = 16;
+constexpr int kGrid = kImg / kPatch;          // 14
+constexpr int kPatches = kGrid * kGrid;       // 196
+constexpr int kTokens = kPatches + 1;         // 197
+constexpr int kHidden = 768;
+constexpr int kHeads = 12;
+constexpr int kHeadDim = 64;
+constexpr int kFfn = 3072;
+constexpr int kLayers = 12;
+constexpr int kQkv = 3 * kHidden;             // 2304
+constexpr float kLnEps = 1e-5f;
+constexpr int kFrameElems = 3 * kImg * kImg;  // 150528
+
+// ---- error plumbing (no exceptions across the C ABI)
+void set_last_error(const std::string& msg);
+void count_launch(int n = 1);   // every kernel launch of this library is counted (bench.py "gpu_launches")
+
+#define SASVQA_CUDA_CHECK(expr)                                                              \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::sasvqa::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) +    \
+                                     " (" __FILE__ ":" + std::to_string(__LINE__) + ")");    \
+            return 2; /* SASVQA_ERR_CUDA */                                                  \
+        }                                                                                    \
+    } while (0)
+
+#define SASVQA_REQUIRE(cond, msg)                                                            \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            ::sasvqa::set_last_error(std::string(msg) + " [" #cond "]");                     \
+            return 1; /* SASVQA_ERR_INVALID */                                               \
+        }                                                                                    \
+    } while (0)
+
+// ---- epilogue modes of the encoder GEMM
+enum GemmEpilogue : int {
+    EPI_BIAS_BF16 = 0,        // out_bf16 = acc + bias                         (fused q|k|v projection)
+    EPI_BIAS_GELU_BF16 = 1,   // out_bf16 = quick_gelu(acc + bias)             (fc1)
+    EPI_BIAS_RESID_F32 = 2,   // x_f32   += acc + bias  (in place)             (out_proj, fc2)
+    EPI_PATCH_EMBED_F32 = 3,  // x_f32[frame*197 + 1 + p] = acc + pos[1 + p]   (patch embedding)
+};
+
+struct GemmArgs {
+    const __nv_bfloat16* A;   // [M, K] row-major (K contiguous)
+    const __nv_bfloat16* B;   // [N, K] row-major (nn.Linear weight layout)
+    int M, N, K;
+    int epilogue;
+    const float* bias;        // [N]            (modes 0,1,2)
+    const float* pos;         // [197, 768]     (mode 3)
+    __nv_bfloat16* out_bf16;  // [M, N]         (modes 0,1)
+    float* out_f32;           // [M, N] or [frames*197, N] (modes 2,3)
+};
+
+// launchers (each returns 0 or an error code, async on `stream`)
+int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUtensorMap* map_b, int num_sms,
+                        cudaStream_t stream);
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
+int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+int launch_preprocess_u8(const uint8_t* frames_hwc, int n_frames, __nv_bfloat16* patches, cudaStream_t s);
+int launch_patchify_f32(const float* frames_chw, int n_frames, __nv_bfloat16* patches, cudaStream_t s);
+int launch_pre_layernorm(float* x, int n_frames, const float* cls_pos0, const float* gamma, const float* beta,
+                         cudaStream_t s);
+int launch_layernorm_bf16(const float* x, __nv_bfloat16* h, int rows, const float* gamma, const float* beta,
+                          cudaStream_t s);
+int launch_pool_norm(const float* x, int n_frames, const float* gamma, const float* beta, float* feats,
+                     cudaStream_t s);
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, cudaStream_t s);
+int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s);
+int launch_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status,
+                      cudaStream_t s);
+int launch_topk_strided(const float* scores, int B, int T, int ds_rate, int K, int32_t* idx,
+                        const int32_t* only_if_status, cudaStream_t s);
+int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s);
+int launch_gather_f32(const float* frames, const int32_t* idx, int B, int T, int K, int64_t row_elems, float* out,
+                      cudaStream_t s);
+
+// ---- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// x * sigmoid(1.702 x)  (HF "quick_gelu", modeling_git.py GitVisionMLP)
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
+// CLIPImageProcessor arithmetic for one channel value, rounded like torch on the CPU
+// (separate multiply, subtract, divide -- no FMA contraction): (u * (1/255) - mean) / std
+__device__ __forceinline__ float normalize_px(uint32_t u, float mean, float stdv) {
+    return __fdiv_rn(__fsub_rn(__fmul_rn((float)u, 1.0f / 255.0f), mean), stdv);
+}
+
+__device__ __forceinline__ float px_mean(int c) { return c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f); }
+__device__ __forceinline__ float px_std(int c) { return c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f); }
+
+#endif  // __CUDACC__
+
+}  // namespace sasvqa

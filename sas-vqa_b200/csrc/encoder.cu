@@ -1,0 +1,525 @@
+// Encoder handle (bf16 weights + workspace + TMA descriptors) and the per-clip-list pipelines.
+// Replaces the model side of the reference's extraction loop:
+//   model.eval().cuda(); DataParallel(...)            src/preprocessing/extract_features.py:45-48
+//   for chunk: model(frames[chunk]) -> mean -> norm   src/preprocessing/datautils/utils.py:39-48
+// One process per GPU; the handle is bound to the device current at creation.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/sasvqa.h"
+#include "common.cuh"
+
+namespace sasvqa {
+
+namespace {
+
+constexpr int kDefaultChunkFrames = 1024;
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+__global__ void fill_i32_kernel(int32_t* p, int32_t v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// profiling scopes (bench.py roofline): CUDA-event pairs around each stage's launches
+enum ProfKind {
+    PK_PREPROCESS = 0, PK_GEMM_PATCH, PK_PRE_LN, PK_LN, PK_GEMM_QKV, PK_ATTENTION, PK_GEMM_OUT, PK_GEMM_FC1,
+    PK_GEMM_FC2, PK_POOL, PK_SCORES, PK_SELECT, PK_GATHER, PK_COUNT
+};
+struct ProfRec {
+    int kind;
+    cudaEvent_t a, b;
+};
+
+struct Layer {
+    __nv_bfloat16 *w_qkv, *w_out, *w_fc1, *w_fc2;
+    float *b_qkv, *b_out, *b_fc1, *b_fc2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    CUtensorMap m_qkv, m_out, m_fc1, m_fc2;
+};
+
+}  // namespace
+
+}  // namespace sasvqa
+
+using namespace sasvqa;
+
+struct SasvqaEncoder {
+    int device = 0;
+    int num_sms = 148;
+    int chunk_frames = 0;
+    bool use_simt = false;           // SASVQA_DEBUG_SIMT_GEMM=1: bisecting aid, never set in production
+    // weights (one arena each for bf16 matrices and fp32 vectors)
+    __nv_bfloat16* arena_bf16 = nullptr;
+    float* arena_f32 = nullptr;
+    __nv_bfloat16* w_patch = nullptr;
+    float *pos = nullptr, *cls_pos0 = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr;
+    Layer L[kLayers];
+    CUtensorMap m_patch_w;
+    // workspace for one chunk
+    float* x = nullptr;               // [chunk*197, 768]  fp32 residual stream
+    __nv_bfloat16* h = nullptr;       // [chunk*197, 768]  LN output / attention output
+    __nv_bfloat16* big = nullptr;     // [chunk*197, 3072] qkv (as [.,2304]) / fc1 output / patch matrix (as [chunk*196,768])
+    CUtensorMap m_h, m_big_fc, m_big_patch;
+    // scratch for the whole-path entry points (grown on demand)
+    float* feats = nullptr;
+    size_t feats_cap = 0;
+    float* lcl = nullptr;
+    size_t lcl_cap = 0;
+    // host-buffer pipeline
+    cudaStream_t h2d_stream = nullptr, compute_stream = nullptr, d2h_stream = nullptr;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    size_t stage_cap[2] = {0, 0};
+    float* out_stage[2] = {nullptr, nullptr};
+    size_t out_stage_cap[2] = {0, 0};
+    int32_t* idx_stage[2] = {nullptr, nullptr};
+    size_t idx_stage_cap[2] = {0, 0};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    // optional per-stage timing
+    bool profile = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace sasvqa {
+
+namespace {
+
+struct Scope {
+    SasvqaEncoder* e;
+    int kind;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t take(SasvqaEncoder* e) {
+        if (!e->ev_pool.empty()) {
+            cudaEvent_t ev = e->ev_pool.back();
+            e->ev_pool.pop_back();
+            return ev;
+        }
+        cudaEvent_t ev = nullptr;
+        cudaEventCreate(&ev);
+        return ev;
+    }
+    Scope(SasvqaEncoder* e_, int kind_, cudaStream_t s_) : e(e_), kind(kind_), s(s_) {
+        if (e->profile) {
+            a = take(e);
+            b = take(e);
+            cudaEventRecord(a, s);
+        }
+    }
+    ~Scope() {
+        if (e->profile) {
+            cudaEventRecord(b, s);
+            e->prof.push_back({kind, a, b});
+        }
+    }
+};
+
+int gemm(SasvqaEncoder* e, int kind, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, cudaStream_t s) {
+    Scope sc(e, kind, s);
+    if (e->use_simt) return launch_gemm_simt(g, s);
+    return launch_gemm_tcgen05(g, ma, mb, e->num_sms, s);
+}
+
+// encode `n` frames whose bf16 patch matrix is `patches` (map_patches describes it); leaves the
+// hidden state after `n_layers` blocks in e->x
+int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorMap* map_patches, int n, int n_layers,
+                 cudaStream_t s) {
+    const int M = n * kTokens;
+    int rc;
+    GemmArgs g{};
+    g.A = patches; g.B = e->w_patch; g.M = n * kPatches; g.N = kHidden; g.K = kHidden;
+    g.epilogue = EPI_PATCH_EMBED_F32; g.pos = e->pos; g.out_f32 = e->x;
+    if ((rc = gemm(e, PK_GEMM_PATCH, g, map_patches, &e->m_patch_w, s))) return rc;
+    {
+        Scope sc(e, PK_PRE_LN, s);
+        if ((rc = launch_pre_layernorm(e->x, n, e->cls_pos0, e->pre_g, e->pre_b, s))) return rc;
+    }
+    for (int l = 0; l < n_layers; ++l) {
+        Layer& L = e->L[l];
+        {
+            Scope sc(e, PK_LN, s);
+            if ((rc = launch_layernorm_bf16(e->x, e->h, M, L.ln1_g, L.ln1_b, s))) return rc;
+        }
+        g = GemmArgs{};
+        g.A = e->h; g.B = L.w_qkv; g.M = M; g.N = kQkv; g.K = kHidden;
+        g.epilogue = EPI_BIAS_BF16; g.bias = L.b_qkv; g.out_bf16 = e->big;
+        if ((rc = gemm(e, PK_GEMM_QKV, g, &e->m_h, &L.m_qkv, s))) return rc;
+        {
+            Scope sc(e, PK_ATTENTION, s);
+            if ((rc = launch_attention(e->big, e->h, n, s))) return rc;
+        }
+        g = GemmArgs{};
+        g.A = e->h; g.B = L.w_out; g.M = M; g.N = kHidden; g.K = kHidden;
+        g.epilogue = EPI_BIAS_RESID_F32; g.bias = L.b_out; g.out_f32 = e->x;
+        if ((rc = gemm(e, PK_GEMM_OUT, g, &e->m_h, &L.m_out, s))) return rc;
+        {
+            Scope sc(e, PK_LN, s);
+            if ((rc = launch_layernorm_bf16(e->x, e->h, M, L.ln2_g, L.ln2_b, s))) return rc;
+        }
+        g = GemmArgs{};
+        g.A = e->h; g.B = L.w_fc1; g.M = M; g.N = kFfn; g.K = kHidden;
+        g.epilogue = EPI_BIAS_GELU_BF16; g.bias = L.b_fc1; g.out_bf16 = e->big;
+        if ((rc = gemm(e, PK_GEMM_FC1, g, &e->m_h, &L.m_fc1, s))) return rc;
+        g = GemmArgs{};
+        g.A = e->big; g.B = L.w_fc2; g.M = M; g.N = kHidden; g.K = kFfn;
+        g.epilogue = EPI_BIAS_RESID_F32; g.bias = L.b_fc2; g.out_f32 = e->x;
+        if ((rc = gemm(e, PK_GEMM_FC2, g, &e->m_big_fc, &L.m_fc2, s))) return rc;
+    }
+    return 0;
+}
+
+int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) SASVQA_CUDA_CHECK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    SASVQA_CUDA_CHECK(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+}  // namespace
+
+int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames, SasvqaEncoder** out) {
+    SASVQA_REQUIRE(out != nullptr && params_host != nullptr, "null argument");
+    SASVQA_REQUIRE(n_params == SASVQA_NUM_ENCODER_PARAMS, "state dict must hold 85 799 424 fp32 values (ViT-B/16)");
+    if (chunk_frames <= 0) chunk_frames = kDefaultChunkFrames;
+    SasvqaEncoder* e = new SasvqaEncoder();
+    auto fail = [&](int rc) { sasvqa_encoder_destroy(e); return rc; };
+#define TRY(expr) do { int _rc = (expr); if (_rc) return fail(_rc); } while (0)
+#define TRYCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(SASVQA_ERR_CUDA); } } while (0)
+    TRYCUDA(cudaGetDevice(&e->device));
+    cudaDeviceProp prop;
+    TRYCUDA(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major != 10) {
+        set_last_error("sasvqa_b200 needs an sm_100a GPU (B200); found compute capability " +
+                       std::to_string(prop.major) + "." + std::to_string(prop.minor));
+        return fail(SASVQA_ERR_INVALID);
+    }
+    e->num_sms = prop.multiProcessorCount;
+    e->chunk_frames = chunk_frames;
+    const char* dbg = getenv("SASVQA_DEBUG_SIMT_GEMM");
+    e->use_simt = dbg != nullptr && dbg[0] == '1';
+
+    // ---- upload the fp32 state dict once, carve bf16 matrices / fp32 vectors out of it on device
+    float* raw = nullptr;
+    TRYCUDA(cudaMalloc(&raw, n_params * sizeof(float)));
+    if (cudaMemcpy(raw, params_host, n_params * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(raw);
+        set_last_error("uploading encoder parameters failed");
+        return fail(SASVQA_ERR_CUDA);
+    }
+    const size_t n_mat = (size_t)kHidden * kHidden + (size_t)kLayers * ((size_t)kQkv * kHidden + (size_t)kHidden * kHidden +
+                                                                          2 * (size_t)kFfn * kHidden);
+    const size_t n_vec = (size_t)kTokens * kHidden + kHidden + 4 * kHidden +
+                         (size_t)kLayers * (kQkv + kHidden + kFfn + kHidden + 4 * kHidden);
+    if (cudaMalloc(&e->arena_bf16, n_mat * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMalloc(&e->arena_f32, n_vec * sizeof(float)) != cudaSuccess) {
+        cudaFree(raw);
+        set_last_error("allocating encoder weights failed");
+        return fail(SASVQA_ERR_NOMEM);
+    }
+    __nv_bfloat16* mp = e->arena_bf16;
+    float* vp = e->arena_f32;
+    const float* rp = raw;
+    auto take_mat = [&](size_t n) {      // fp32 -> bf16 matrix
+        __nv_bfloat16* dst = mp;
+        f32_to_bf16_kernel<<<592, 256>>>(rp, dst, (long long)n);
+        mp += n; rp += n;
+        return dst;
+    };
+    auto take_vec = [&](size_t n) {      // fp32 vector copy
+        float* dst = vp;
+        cudaMemcpyAsync(dst, rp, n * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+        vp += n; rp += n;
+        return dst;
+    };
+    const float* cls_raw = rp; rp += kHidden;                       // class_embedding
+    e->w_patch = take_mat((size_t)kHidden * kHidden);               // patch_embedding.weight [768, 3*16*16]
+    e->pos = take_vec((size_t)kTokens * kHidden);                   // position_embedding.weight
+    e->cls_pos0 = vp; vp += kHidden;
+    add_vec_kernel<<<3, 256>>>(cls_raw, e->pos, e->cls_pos0, kHidden);
+    e->pre_g = take_vec(kHidden);
+    e->pre_b = take_vec(kHidden);
+    for (int l = 0; l < kLayers; ++l) {
+        Layer& L = e->L[l];
+        // HF order: k, v, q, out.  Fused projection rows are ordered q | k | v.
+        L.w_qkv = mp; mp += (size_t)kQkv * kHidden;
+        L.b_qkv = vp; vp += kQkv;
+        const size_t ww = (size_t)kHidden * kHidden;
+        const int slot_of[3] = {1, 2, 0};   // k -> slot 1, v -> slot 2, q -> slot 0
+        for (int j = 0; j < 3; ++j) {
+            f32_to_bf16_kernel<<<592, 256>>>(rp, L.w_qkv + slot_of[j] * ww, (long long)ww);
+            rp += ww;
+            cudaMemcpyAsync(L.b_qkv + slot_of[j] * kHidden, rp, kHidden * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+            rp += kHidden;
+        }
+        L.w_out = take_mat(ww);
+        L.b_out = take_vec(kHidden);
+        L.ln1_g = take_vec(kHidden);
+        L.ln1_b = take_vec(kHidden);
+        L.w_fc1 = take_mat((size_t)kFfn * kHidden);
+        L.b_fc1 = take_vec(kFfn);
+        L.w_fc2 = take_mat((size_t)kHidden * kFfn);
+        L.b_fc2 = take_vec(kHidden);
+        L.ln2_g = take_vec(kHidden);
+        L.ln2_b = take_vec(kHidden);
+    }
+    e->post_g = take_vec(kHidden);
+    e->post_b = take_vec(kHidden);
+    cudaError_t ce = cudaDeviceSynchronize();
+    cudaFree(raw);
+    if (ce != cudaSuccess || (size_t)(rp - raw) != n_params || (size_t)(mp - e->arena_bf16) != n_mat ||
+        (size_t)(vp - e->arena_f32) != n_vec) {
+        set_last_error(std::string("encoder weight conversion failed: ") + cudaGetErrorString(ce));
+        return fail(SASVQA_ERR_CUDA);
+    }
+
+    // ---- workspace + TMA descriptors
+    const size_t rows = (size_t)chunk_frames * kTokens;
+    if (cudaMalloc(&e->x, rows * kHidden * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->h, rows * kHidden * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMalloc(&e->big, rows * kFfn * sizeof(__nv_bfloat16)) != cudaSuccess) {
+        set_last_error("allocating encoder workspace failed (lower chunk_frames)");
+        return fail(SASVQA_ERR_NOMEM);
+    }
+    TRYCUDA(cudaMemset(e->h, 0, rows * kHidden * sizeof(__nv_bfloat16)));
+    TRYCUDA(cudaMemset(e->big, 0, rows * kFfn * sizeof(__nv_bfloat16)));
+    TRY(make_tensor_map_bf16_kmajor(&e->m_patch_w, e->w_patch, kHidden, kHidden, 256));
+    TRY(make_tensor_map_bf16_kmajor(&e->m_h, e->h, rows, kHidden, 128));
+    TRY(make_tensor_map_bf16_kmajor(&e->m_big_fc, e->big, rows, kFfn, 128));
+    TRY(make_tensor_map_bf16_kmajor(&e->m_big_patch, e->big, (uint64_t)chunk_frames * kPatches, kHidden, 128));
+    for (int l = 0; l < kLayers; ++l) {
+        Layer& L = e->L[l];
+        TRY(make_tensor_map_bf16_kmajor(&L.m_qkv, L.w_qkv, kQkv, kHidden, 256));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_out, L.w_out, kHidden, kHidden, 256));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_fc1, L.w_fc1, kFfn, kHidden, 256));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_fc2, L.w_fc2, kHidden, kFfn, 256));
+    }
+    TRYCUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        TRYCUDA(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+        TRYCUDA(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
+        TRYCUDA(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+    }
+#undef TRY
+#undef TRYCUDA
+    *out = e;
+    return 0;
+}
+
+int encoder_chunk_frames(const SasvqaEncoder* e) { return e ? e->chunk_frames : 0; }
+
+int profile_enable(SasvqaEncoder* e, int on) {
+    SASVQA_REQUIRE(e != nullptr, "null encoder");
+    e->profile = on != 0;
+    return 0;
+}
+
+// Sums the recorded stage timings (ms) and launch-scope counts per ProfKind, then resets.
+int profile_read(SasvqaEncoder* e, double* ms, int64_t* scopes, int n_kinds) {
+    SASVQA_REQUIRE(e != nullptr && ms != nullptr && scopes != nullptr && n_kinds >= PK_COUNT, "bad arguments");
+    SASVQA_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int k = 0; k < n_kinds; ++k) {
+        ms[k] = 0.0;
+        scopes[k] = 0;
+    }
+    for (const ProfRec& r : e->prof) {
+        float t = 0.f;
+        SASVQA_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.kind] += t;
+        scopes[r.kind] += 1;
+        e->ev_pool.push_back(r.a);
+        e->ev_pool.push_back(r.b);
+    }
+    e->prof.clear();
+    return 0;
+}
+
+void encoder_destroy(SasvqaEncoder* e) {
+    if (!e) return;
+    cudaFree(e->arena_bf16); cudaFree(e->arena_f32);
+    cudaFree(e->x); cudaFree(e->h); cudaFree(e->big);
+    cudaFree(e->feats); cudaFree(e->lcl);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(e->stage[i]); cudaFree(e->out_stage[i]); cudaFree(e->idx_stage[i]);
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
+    for (const ProfRec& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
+    if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
+    if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
+    delete e;
+}
+
+// patches (caller memory) -> feats, any n
+int encoder_fwd(SasvqaEncoder* e, const __nv_bfloat16* patches, int n_frames, float* feats, cudaStream_t s) {
+    SASVQA_REQUIRE(e != nullptr && n_frames >= 0, "bad arguments");
+    for (int f0 = 0; f0 < n_frames; f0 += e->chunk_frames) {
+        const int n = std::min(e->chunk_frames, n_frames - f0);
+        const __nv_bfloat16* p = patches + (size_t)f0 * kPatches * kHidden;
+        CUtensorMap mp;
+        int rc = make_tensor_map_bf16_kmajor(&mp, p, (uint64_t)n * kPatches, kHidden, 128);
+        if (rc) return rc;
+        if ((rc = encode_chunk(e, p, &mp, n, kLayers, s))) return rc;
+        {
+            Scope sc(e, PK_POOL, s);
+            if ((rc = launch_pool_norm(e->x, n, e->post_g, e->post_b, feats + (size_t)f0 * kHidden, s))) return rc;
+        }
+    }
+    return 0;
+}
+
+int encoder_fwd_hidden(SasvqaEncoder* e, const __nv_bfloat16* patches, int n_frames, int n_layers, float* hidden,
+                       cudaStream_t s) {
+    SASVQA_REQUIRE(e != nullptr && n_frames > 0 && n_frames <= e->chunk_frames, "n_frames must be in (0, chunk_frames]");
+    SASVQA_REQUIRE(n_layers >= 0 && n_layers <= kLayers, "n_layers out of range");
+    CUtensorMap mp;
+    int rc = make_tensor_map_bf16_kmajor(&mp, patches, (uint64_t)n_frames * kPatches, kHidden, 128);
+    if (rc) return rc;
+    if ((rc = encode_chunk(e, patches, &mp, n_frames, n_layers, s))) return rc;
+    SASVQA_CUDA_CHECK(cudaMemcpyAsync(hidden, e->x, (size_t)n_frames * kTokens * kHidden * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// frames (uint8 HWC or fp32 CHW, device) -> feats [n_frames, 768], chunked through the workspace
+static int encode_frames(SasvqaEncoder* e, const uint8_t* u8, const float* f32, long long n_frames, float* feats,
+                         cudaStream_t s) {
+    for (long long f0 = 0; f0 < n_frames; f0 += e->chunk_frames) {
+        const int n = (int)std::min<long long>(e->chunk_frames, n_frames - f0);
+        int rc;
+        {
+            Scope sc(e, PK_PREPROCESS, s);
+            if (u8) rc = launch_preprocess_u8(u8 + (size_t)f0 * kFrameElems, n, e->big, s);
+            else rc = launch_patchify_f32(f32 + (size_t)f0 * kFrameElems, n, e->big, s);
+            if (rc) return rc;
+        }
+        if ((rc = encode_chunk(e, e->big, &e->m_big_patch, n, kLayers, s))) return rc;
+        {
+            Scope sc(e, PK_POOL, s);
+            if ((rc = launch_pool_norm(e->x, n, e->post_g, e->post_b, feats + (size_t)f0 * kHidden, s))) return rc;
+        }
+    }
+    return 0;
+}
+
+int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int K, int W, int32_t* idx,
+                      int32_t* status, float* lcl_out, float* feats_out, float* sampled, cudaStream_t s) {
+    SASVQA_REQUIRE(e != nullptr && idx != nullptr && status != nullptr, "null argument");
+    SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 1, "bad B/T/K");
+    SASVQA_REQUIRE(W >= -1, "W must be >= 0, or -1 for the adaptive width T / 20");
+    if (B == 0) return 0;
+    if (W == -1) W = T / 20;                                    // utils.py:32-33
+    if (T == 0) {                                               // utils.py:50-52: zero frames, 'Zeros'
+        fill_i32_kernel<<<(B + 255) / 256, 256, 0, s>>>(status, SASVQA_STATUS_EMPTY, B);
+        fill_i32_kernel<<<(B * K + 255) / 256, 256, 0, s>>>(idx, -1, B * K);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        if (sampled) SASVQA_CUDA_CHECK(cudaMemsetAsync(sampled, 0, (size_t)B * K * kFrameElems * sizeof(float), s));
+        return 0;
+    }
+    int rc;
+    const size_t nf = (size_t)B * T;
+    float* feats = feats_out;
+    if (!feats) {
+        if ((rc = grow((void**)&e->feats, &e->feats_cap, nf * kHidden * sizeof(float)))) return rc;
+        feats = e->feats;
+    }
+    float* lcl = lcl_out;
+    if (!lcl) {
+        if ((rc = grow((void**)&e->lcl, &e->lcl_cap, nf * sizeof(float)))) return rc;
+        lcl = e->lcl;
+    }
+    if ((rc = encode_frames(e, u8, f32, (long long)nf, feats, s))) return rc;
+    {
+        Scope sc(e, PK_SCORES, s);
+        if ((rc = launch_mdf_scores(feats, B, T, W, lcl, nullptr, s))) return rc;
+    }
+    {
+        Scope sc(e, PK_SELECT, s);
+        if ((rc = launch_mdf_select(lcl, B, T, K, W, idx, status, s))) return rc;
+    }
+    if (sampled) {
+        Scope sc(e, PK_GATHER, s);
+        if (u8) rc = launch_gather_u8(u8, idx, B, T, K, sampled, s);
+        else rc = launch_gather_f32(f32, idx, B, T, K, kFrameElems, sampled, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// Host-buffer pipeline: groups of whole clips; H2D (h2d_stream), compute (compute_stream) and
+// D2H (d2h_stream) of consecutive groups overlap through two staging slots.
+int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int K, int W, int32_t* idx_host,
+                    int32_t* status_host, float* sampled_host) {
+    SASVQA_REQUIRE(e != nullptr && idx_host != nullptr && status_host != nullptr, "null argument");
+    SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 1 && W >= -1, "bad B/T/K/W");
+    if (B == 0) return 0;
+    if (T == 0) {
+        for (int b = 0; b < B; ++b) status_host[b] = SASVQA_STATUS_EMPTY;
+        for (long long i = 0; i < (long long)B * K; ++i) idx_host[i] = -1;
+        if (sampled_host) memset(sampled_host, 0, (size_t)B * K * kFrameElems * sizeof(float));
+        return 0;
+    }
+    SASVQA_REQUIRE(clips != nullptr, "null clips");
+    const int group = std::max(1, e->chunk_frames / T);          // whole clips per group
+    const size_t out_need = sampled_host ? (size_t)group * K * kFrameElems * sizeof(float) : 0;
+    int rc;
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = grow((void**)&e->stage[i], &e->stage_cap[i], (size_t)group * T * kFrameElems))) return rc;
+        if (out_need && (rc = grow((void**)&e->out_stage[i], &e->out_stage_cap[i], out_need))) return rc;
+        if ((rc = grow((void**)&e->idx_stage[i], &e->idx_stage_cap[i], (size_t)group * (K + 1) * sizeof(int32_t))))
+            return rc;
+    }
+    const int n_groups = (B + group - 1) / group;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int slot = gi & 1;
+        const int b0 = gi * group, nb = std::min(group, B - b0);
+        // stage[slot] is free once group gi-2 has finished computing (its gather reads the frames)
+        if (gi >= 2) SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->h2d_stream, e->ev_comp[slot], 0));
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->stage[slot], clips + (size_t)b0 * T * kFrameElems,
+                                          (size_t)nb * T * kFrameElems, cudaMemcpyHostToDevice, e->h2d_stream));
+        SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_in[slot], e->h2d_stream));
+        SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->compute_stream, e->ev_in[slot], 0));
+        // idx/out staging of this slot is free once group gi-2's results are on the host
+        if (gi >= 2) SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->compute_stream, e->ev_out[slot], 0));
+        int32_t* d_idx = e->idx_stage[slot];
+        int32_t* d_status = d_idx + (size_t)group * K;
+        float* d_out = sampled_host ? e->out_stage[slot] : nullptr;
+        if ((rc = mdf_sample_device(e, e->stage[slot], nullptr, nb, T, K, W, d_idx, d_status, nullptr, nullptr, d_out,
+                                    e->compute_stream)))
+            return rc;
+        SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_comp[slot], e->compute_stream));
+        SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->ev_comp[slot], 0));
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host + (size_t)b0 * K, d_idx, (size_t)nb * K * sizeof(int32_t),
+                                          cudaMemcpyDeviceToHost, e->d2h_stream));
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(status_host + b0, d_status, (size_t)nb * sizeof(int32_t),
+                                          cudaMemcpyDeviceToHost, e->d2h_stream));
+        if (sampled_host)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(sampled_host + (size_t)b0 * K * kFrameElems, d_out,
+                                              (size_t)nb * K * kFrameElems * sizeof(float), cudaMemcpyDeviceToHost,
+                                              e->d2h_stream));
+        SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_out[slot], e->d2h_stream));
+    }
+    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
+    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->compute_stream));
+    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->h2d_stream));
+    return 0;
+}
+
+}  // namespace sasvqa

@@ -1,0 +1,323 @@
+// Scoring and selection stages of the samplers (all per clip, HBM/latency bound):
+//   K3b/K4a  windowed mean cosine similarity  (reference src/preprocessing/datautils/utils.py:55-61)
+//   K4b      greedy best-first interval selection with the +-W spacing rule (utils.py:63-88)
+//   K4b'     plain top-K fallback                                            (utils.py:91-93)
+//   K4c      strided top-K for the MIF sampler          (src/preprocessing/gen_sample.py:87-88)
+// Tie rule everywhere: among exactly equal scores the LOWEST index wins (argmax semantics); the
+// reference's torch.topk order among equal values is implementation-defined (see oracle/mdf.py).
+#include "common.cuh"
+
+namespace sasvqa {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// lcl_avg[b, i] = (sum_{j=i-W}^{i+W-1} <f_i, f_j> - 1) / (2W - 1) for W <= i < T-W, else 0.
+// Only the band of the Gram matrix the reference ever reads is computed (it builds all T x T).
+// One warp per (clip, frame): f_i stays in registers (24 floats/lane), the 2W neighbours stream
+// through L1/L2.  Every dot product is reduced on its own, then the 2W dots are summed in window
+// order, mirroring the reference's "Gram row slice, then sum".
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mdf_scores_kernel(const float* __restrict__ feats, int B, int T, int W,
+                                                          float* __restrict__ lcl) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (long long)B * T) return;
+    const int i = (int)(wid % T);
+    const long long b = wid / T;
+    if (i < W || i >= T - W) {
+        if (lane == 0) lcl[wid] = 0.0f;
+        return;
+    }
+    const float4* fi = reinterpret_cast<const float4*>(feats + (b * T + i) * kHidden);
+    float4 a[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[j] = __ldg(fi + lane + 32 * j);
+    float window = 0.0f;
+    for (int jj = i - W; jj < i + W; ++jj) {
+        const float4* fj = reinterpret_cast<const float4*>(feats + (b * T + jj) * kHidden);
+        float d = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float4 v = __ldg(fj + lane + 32 * j);
+            d = fmaf(a[j].x, v.x, d);
+            d = fmaf(a[j].y, v.y, d);
+            d = fmaf(a[j].z, v.z, d);
+            d = fmaf(a[j].w, v.w, d);
+        }
+        window = __fadd_rn(window, warp_sum(d));
+    }
+    if (lane == 0) lcl[wid] = __fdiv_rn(__fsub_rn(window, 1.0f), (float)(2 * W - 1));
+}
+
+// Optional full Gram (debug / inspection output of sasvqa_mdf_scores): S[b] = F_b F_b^T.
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ feats, int T, float* __restrict__ gram) {
+    __shared__ float fa[16][33], fb[16][33];
+    const long long b = blockIdx.z;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int r = blockIdx.y * 16 + ty, c = blockIdx.x * 16 + tx;
+    const float* F = feats + b * T * (long long)kHidden;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < kHidden; k0 += 32) {
+        for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+            const int rr = e >> 5, kk = e & 31;
+            const int ra = blockIdx.y * 16 + rr, rb = blockIdx.x * 16 + rr;
+            fa[rr][kk] = ra < T ? F[(long long)ra * kHidden + k0 + kk] : 0.f;
+            fb[rr][kk] = rb < T ? F[(long long)rb * kHidden + k0 + kk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) acc = fmaf(fa[ty][kk], fb[tx][kk], acc);
+        __syncthreads();
+    }
+    if (r < T && c < T) gram[(b * T + r) * (long long)T + c] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-wide first-argmax of v[lo, hi): highest value, lowest index among equals.  hi > lo.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_first_argmax(const float* __restrict__ v, int lo, int hi, int lane, float* best_v) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lo + lane; i < hi; i += 32) {
+        const float x = v[i];
+        if (x > bv || bi == 0x7fffffff) {
+            bv = x;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    *best_v = bv;
+    return bi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4b: one warp per clip.  Open intervals live in shared memory as (score, l, r, argmax); the
+// next pick is the interval with the highest score, smaller left edge on ties -- exactly the
+// order in which the reference's heap of (-v, (l, r), idx) tuples pops.  At most K+1 intervals
+// are ever open.  status: 0 = K picks found, 1 = fewer than K (caller runs the top-K fallback),
+// 3 = T < K (the reference's fallback raises).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) mdf_greedy_kernel(const float* __restrict__ lcl_all, int T, int K, int W,
+                                                         int32_t* __restrict__ idx_all, int32_t* __restrict__ status) {
+    extern __shared__ int32_t sel_smem[];
+    float* iv_score = reinterpret_cast<float*>(sel_smem);
+    int32_t* iv_l = sel_smem + (K + 2);
+    int32_t* iv_r = sel_smem + 2 * (K + 2);
+    int32_t* iv_p = sel_smem + 3 * (K + 2);
+    const int lane = threadIdx.x;
+    const long long b = blockIdx.x;
+    const float* lcl = lcl_all + b * T;
+    int32_t* out = idx_all + b * K;
+
+    int n_open = 0;
+    auto push = [&](int l, int r) {
+        float v;
+        const int p = warp_first_argmax(lcl, l, r, lane, &v);
+        if (lane == 0) {
+            iv_score[n_open] = v;
+            iv_l[n_open] = l;
+            iv_r[n_open] = r;
+            iv_p[n_open] = p;
+        }
+        ++n_open;
+        __syncwarp();
+    };
+
+    float v0;
+    const int top = warp_first_argmax(lcl, 0, T, lane, &v0);
+    if (lane == 0) out[0] = top;
+    int n_picks = 1;
+    if (top - W > 0) push(0, top - W);
+    if (top + W < T) push(top + W, T);
+    while (n_picks < K && n_open > 0) {
+        // best open interval: max score, then min l
+        float bv = -INFINITY;
+        int bl = 0x7fffffff, bj = -1;
+        for (int j = lane; j < n_open; j += 32) {
+            const float s = iv_score[j];
+            const int l = iv_l[j];
+            if (bj < 0 || s > bv || (s == bv && l < bl)) {
+                bv = s;
+                bl = l;
+                bj = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (oj >= 0 && (bj < 0 || ov > bv || (ov == bv && ol < bl))) {
+                bv = ov;
+                bl = ol;
+                bj = oj;
+            }
+        }
+        const int l = iv_l[bj], r = iv_r[bj], p = iv_p[bj];
+        __syncwarp();
+        if (lane == 0) {
+            out[n_picks] = p;
+            const int last = n_open - 1;     // remove by moving the last interval into the hole
+            iv_score[bj] = iv_score[last];
+            iv_l[bj] = iv_l[last];
+            iv_r[bj] = iv_r[last];
+            iv_p[bj] = iv_p[last];
+        }
+        --n_open;
+        ++n_picks;
+        __syncwarp();
+        if (p - W > l) push(l, p - W);
+        if (p + W < r) push(p + W, r);
+    }
+    if (lane == 0) status[b] = (n_picks >= K) ? 0 : (T < K ? 3 : 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-K (descending score, lowest index first among equals) over v[0 : T : stride].
+// Sort key: (~orderable(score) << 32) | position, ascending.  -0.0 == +0.0, NaN sorts first
+// (torch.topk treats NaN as the largest value).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t topk_key(float x, uint32_t pos) {
+    uint32_t u = __float_as_uint(x == 0.0f ? 0.0f : x);
+    if (x != x) u = 0x7fffffffu;                                // canonical +NaN, above +inf
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // order-preserving map to unsigned
+    return ((uint64_t)(~u) << 32) | pos;
+}
+
+// one CTA per row; n = ceil(T / stride) <= n_pad (power of two) keys bitonic-sorted in shared memory
+__global__ void __launch_bounds__(256) topk_bitonic_kernel(const float* __restrict__ scores, int T, int stride, int K,
+                                                            int n_pad, int32_t* __restrict__ idx_all,
+                                                            const int32_t* __restrict__ only_if_status) {
+    extern __shared__ uint64_t keys[];
+    const long long b = blockIdx.x;
+    if (only_if_status != nullptr && only_if_status[b] != 1) return;
+    const int n = (T + stride - 1) / stride;
+    const float* v = scores + b * T;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+        keys[i] = i < n ? topk_key(v[(long long)i * stride], (uint32_t)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+                const int partner = i ^ j;
+                if (partner > i) {
+                    const uint64_t a = keys[i], c = keys[partner];
+                    const bool up = (i & k) == 0;
+                    if ((a > c) == up) {
+                        keys[i] = c;
+                        keys[partner] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+        idx_all[b * K + i] = (int32_t)((uint32_t)(keys[i] & 0xffffffffu)) * stride;
+}
+
+// any T: K rounds of a block-wide "smallest key greater than the previous pick"
+__global__ void __launch_bounds__(256) topk_rounds_kernel(const float* __restrict__ scores, int T, int stride, int K,
+                                                           int32_t* __restrict__ idx_all,
+                                                           const int32_t* __restrict__ only_if_status) {
+    __shared__ uint64_t red[8];
+    __shared__ uint64_t prev_s;
+    const long long b = blockIdx.x;
+    if (only_if_status != nullptr && only_if_status[b] != 1) return;
+    const int n = (T + stride - 1) / stride;
+    const float* v = scores + b * T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t prev = 0;
+    bool have_prev = false;
+    for (int round = 0; round < K; ++round) {
+        uint64_t best = ~0ull;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t key = topk_key(v[(long long)i * stride], (uint32_t)i);
+            if ((!have_prev || key > prev) && key < best) best = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if (lane == 0) red[warp] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t m = red[0];
+            for (int w = 1; w < 8; ++w) m = red[w] < m ? red[w] : m;
+            prev_s = m;
+            idx_all[b * K + round] = (int32_t)((uint32_t)(m & 0xffffffffu)) * stride;
+        }
+        __syncthreads();
+        prev = prev_s;
+        have_prev = true;
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s) {
+    if (B == 0 || T == 0) return 0;
+    SASVQA_REQUIRE(W >= 0, "W must be >= 0 here (resolve W = -1 to T / 20 on the host)");
+    SASVQA_REQUIRE(((uintptr_t)feats & 15) == 0, "feats must be 16-byte aligned");
+    const long long warps = (long long)B * T;
+    const long long blocks = (warps + 7) / 8;
+    SASVQA_REQUIRE(blocks < 2147483647LL, "too many frames for one scores launch");
+    mdf_scores_kernel<<<(unsigned)blocks, 256, 0, s>>>(feats, B, T, W, lcl_avg);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    if (gram != nullptr) {
+        SASVQA_REQUIRE(B <= 65535, "gram output supports at most 65535 clips per call");
+        dim3 grid((T + 15) / 16, (T + 15) / 16, B);
+        gram_kernel<<<grid, 256, 0, s>>>(feats, T, gram);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    }
+    return 0;
+}
+
+int launch_topk_strided(const float* scores, int B, int T, int ds_rate, int K, int32_t* idx,
+                        const int32_t* only_if_status, cudaStream_t s) {
+    if (B == 0 || K == 0) return 0;
+    SASVQA_REQUIRE(ds_rate >= 1, "ds_rate must be >= 1");
+    const int n = (T + ds_rate - 1) / ds_rate;
+    SASVQA_REQUIRE(K <= n, "selected index k out of range");
+    int n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    if (n_pad <= 4096) {
+        topk_bitonic_kernel<<<B, 256, n_pad * sizeof(uint64_t), s>>>(scores, T, ds_rate, K, n_pad, idx, only_if_status);
+    } else {
+        topk_rounds_kernel<<<B, 256, 0, s>>>(scores, T, ds_rate, K, idx, only_if_status);
+    }
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status,
+                      cudaStream_t s) {
+    if (B == 0) return 0;
+    SASVQA_REQUIRE(T >= 1 && K >= 1 && W >= 0, "mdf_select needs T >= 1, K >= 1, W >= 0");
+    SASVQA_REQUIRE(K <= 2048, "K too large");
+    const size_t smem = 4 * (size_t)(K + 2) * sizeof(int32_t);
+    mdf_greedy_kernel<<<B, 32, smem, s>>>(lcl_avg, T, K, W, idx, status);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    if (T >= K) {   // fallback rows (status == 1): discard the greedy picks, plain top-K (utils.py:91-93)
+        int rc = launch_topk_strided(lcl_avg, B, T, 1, K, idx, status, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace sasvqa

@@ -1,0 +1,310 @@
+"""Torch-tensor wrappers over the C ABI, one per entry point of include/sasvqa.h.
+
+Every function allocates outputs with torch (device memory plumbing only), passes raw pointers
+and the current CUDA stream to libsasvqa_b200.so, and raises on any error.  Nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _capi
+from .synth import HIDDEN, IMG, TOKENS, state_dict_keys
+
+FRAME_ELEMS = 3 * IMG * IMG
+PATCHES = (IMG // 16) ** 2
+NUM_PARAMS = 85_799_424
+
+STATUS_OK, STATUS_FALLBACK, STATUS_EMPTY, STATUS_TOO_FEW = 0, 1, 2, 3
+
+
+def _need_cuda(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _capi.SasvqaError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def flatten_state_dict(state_dict: dict) -> torch.Tensor:
+    """fp32 CPU vector in the key order sasvqa_encoder_create expects (HF GitVisionModel order)."""
+    parts = []
+    for name, shape in state_dict_keys():
+        if name not in state_dict:
+            raise KeyError(f"encoder state dict lacks {name!r}; expected a GitVisionModel ViT-B/16 state dict")
+        t = state_dict[name].detach().to("cpu", torch.float32)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: shape {tuple(t.shape)} != {tuple(shape)} (only ViT-B/16 @224 is supported)")
+        parts.append(t.reshape(-1))
+    flat = torch.cat(parts).contiguous()
+    assert flat.numel() == NUM_PARAMS
+    return flat
+
+
+class FrameEncoder:
+    """Owns a SasvqaEncoder handle: bf16 weights, workspace and TMA descriptors on one GPU.
+    The stand-in for `GitVisionModel.from_pretrained(...).eval().cuda()` (extract_features.py:145,45-47)."""
+
+    def __init__(self, state_dict: dict, chunk_frames: int = 0, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        flat = flatten_state_dict(state_dict)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _capi.lib().sasvqa_encoder_create(flat.data_ptr(), flat.numel(), int(chunk_frames),
+                                                   ctypes.byref(handle))
+        _capi.check(rc, "sasvqa_encoder_create")
+        self._h = handle
+        self.chunk_frames = _capi.lib().sasvqa_encoder_chunk_frames(self._h)
+
+    @classmethod
+    def from_model(cls, model, chunk_frames: int = 0, device=None) -> "FrameEncoder":
+        """From an HF GitVisionModel (optionally wrapped in DataParallel like extract_features.py:48)."""
+        inner = getattr(model, "module", model)
+        return cls(inner.state_dict(), chunk_frames=chunk_frames, device=device)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise _capi.SasvqaError("encoder handle already closed")
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            _capi.lib().sasvqa_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- instrumentation
+    PROFILE_KINDS = ("preprocess", "gemm_patch_embed", "pre_layernorm", "layernorm", "gemm_qkv", "attention",
+                     "gemm_out_proj", "gemm_fc1", "gemm_fc2", "pool_norm", "scores", "select", "gather")
+
+    def profile_enable(self, on: bool = True) -> None:
+        _capi.check(_capi.lib().sasvqa_profile_enable(self.handle, int(on)), "sasvqa_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{stage: (total_ms, n_scopes)} accumulated since the last read; synchronises the device."""
+        n = len(self.PROFILE_KINDS)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        _capi.check(_capi.lib().sasvqa_profile_read(self.handle, ms, cnt, n), "sasvqa_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    # ---- K2 + K3a
+    def forward_patches(self, patches: torch.Tensor) -> torch.Tensor:
+        patches = _need_cuda(patches, torch.bfloat16, "patches")
+        n = patches.shape[0] // PATCHES
+        feats = torch.empty(n, HIDDEN, dtype=torch.float32, device=patches.device)
+        with torch.cuda.device(patches.device):
+            _capi.check(_capi.lib().sasvqa_encoder_fwd(self.handle, patches.data_ptr(), n, feats.data_ptr(),
+                                                       _stream(patches)), "sasvqa_encoder_fwd")
+        return feats
+
+    def hidden(self, patches: torch.Tensor, n_layers: int) -> torch.Tensor:
+        patches = _need_cuda(patches, torch.bfloat16, "patches")
+        n = patches.shape[0] // PATCHES
+        out = torch.empty(n, TOKENS, HIDDEN, dtype=torch.float32, device=patches.device)
+        with torch.cuda.device(patches.device):
+            _capi.check(_capi.lib().sasvqa_encoder_fwd_hidden(self.handle, patches.data_ptr(), n, int(n_layers),
+                                                              out.data_ptr(), _stream(patches)),
+                        "sasvqa_encoder_fwd_hidden")
+        return out
+
+    def features_u8(self, frames_hwc: torch.Tensor) -> torch.Tensor:
+        return self.forward_patches(preprocess_u8(frames_hwc))
+
+    def features_f32(self, frames_chw: torch.Tensor) -> torch.Tensor:
+        return self.forward_patches(patchify_f32(frames_chw))
+
+
+# ---- K1
+def preprocess_u8(frames_hwc: torch.Tensor) -> torch.Tensor:
+    frames_hwc = _need_cuda(frames_hwc, torch.uint8, "frames")
+    assert frames_hwc.shape[-3:] == (IMG, IMG, 3), "frames must be [..., 224, 224, 3] uint8"
+    n = frames_hwc.numel() // FRAME_ELEMS
+    patches = torch.empty(n * PATCHES, HIDDEN, dtype=torch.bfloat16, device=frames_hwc.device)
+    with torch.cuda.device(frames_hwc.device):
+        _capi.check(_capi.lib().sasvqa_preprocess_u8(frames_hwc.data_ptr(), n, patches.data_ptr(),
+                                                     _stream(frames_hwc)), "sasvqa_preprocess_u8")
+    return patches
+
+
+def patchify_f32(frames_chw: torch.Tensor) -> torch.Tensor:
+    frames_chw = _need_cuda(frames_chw, torch.float32, "frames")
+    assert frames_chw.shape[-3:] == (3, IMG, IMG), "frames must be [..., 3, 224, 224] fp32"
+    n = frames_chw.numel() // FRAME_ELEMS
+    patches = torch.empty(n * PATCHES, HIDDEN, dtype=torch.bfloat16, device=frames_chw.device)
+    with torch.cuda.device(frames_chw.device):
+        _capi.check(_capi.lib().sasvqa_patchify_f32(frames_chw.data_ptr(), n, patches.data_ptr(),
+                                                    _stream(frames_chw)), "sasvqa_patchify_f32")
+    return patches
+
+
+# ---- K3b + K4a
+def mdf_scores(feats: torch.Tensor, W: int, want_gram: bool = False):
+    feats = _need_cuda(feats, torch.float32, "feats")
+    squeeze = feats.dim() == 2
+    if squeeze:
+        feats = feats.unsqueeze(0)
+    B, T, D = feats.shape
+    assert D == HIDDEN
+    lcl = torch.empty(B, T, dtype=torch.float32, device=feats.device)
+    gram = torch.empty(B, T, T, dtype=torch.float32, device=feats.device) if want_gram else None
+    with torch.cuda.device(feats.device):
+        _capi.check(_capi.lib().sasvqa_mdf_scores(feats.data_ptr(), B, T, int(W), lcl.data_ptr(), _capi.ptr(gram),
+                                                  _stream(feats)), "sasvqa_mdf_scores")
+    if squeeze:
+        lcl = lcl[0]
+        gram = gram[0] if gram is not None else None
+    return (lcl, gram) if want_gram else lcl
+
+
+# ---- K4b
+def mdf_select(lcl_avg: torch.Tensor, K: int, W: int):
+    lcl_avg = _need_cuda(lcl_avg, torch.float32, "lcl_avg")
+    squeeze = lcl_avg.dim() == 1
+    if squeeze:
+        lcl_avg = lcl_avg.unsqueeze(0)
+    B, T = lcl_avg.shape
+    idx = torch.empty(B, K, dtype=torch.int32, device=lcl_avg.device)
+    status = torch.empty(B, dtype=torch.int32, device=lcl_avg.device)
+    with torch.cuda.device(lcl_avg.device):
+        _capi.check(_capi.lib().sasvqa_mdf_select(lcl_avg.data_ptr(), B, T, int(K), int(W), idx.data_ptr(),
+                                                  status.data_ptr(), _stream(lcl_avg)), "sasvqa_mdf_select")
+    return (idx[0], status[0]) if squeeze else (idx, status)
+
+
+# ---- K4c
+def topk_strided(scores: torch.Tensor, K: int, ds_rate: int = 1) -> torch.Tensor:
+    scores = _need_cuda(scores, torch.float32, "scores")
+    squeeze = scores.dim() == 1
+    if squeeze:
+        scores = scores.unsqueeze(0)
+    B, T = scores.shape
+    idx = torch.empty(B, K, dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _capi.check(_capi.lib().sasvqa_topk_strided(scores.data_ptr(), B, T, int(ds_rate), int(K), idx.data_ptr(),
+                                                    _stream(scores)), "sasvqa_topk_strided")
+    return idx[0] if squeeze else idx
+
+
+# ---- K5
+def gather_frames_u8(clips: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    clips = _need_cuda(clips, torch.uint8, "clips")
+    idx = _need_cuda(idx, torch.int32, "idx")
+    B, T = clips.shape[0], clips.shape[1]
+    K = idx.shape[-1]
+    out = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, device=clips.device)
+    with torch.cuda.device(clips.device):
+        _capi.check(_capi.lib().sasvqa_gather_frames_u8(clips.data_ptr(), idx.data_ptr(), B, T, K, out.data_ptr(),
+                                                        _stream(clips)), "sasvqa_gather_frames_u8")
+    return out
+
+
+def gather_frames_f32(frames: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """frames [B, T, ...] fp32, idx [B, K] -> [B, K, ...]."""
+    frames = _need_cuda(frames, torch.float32, "frames")
+    idx = _need_cuda(idx, torch.int32, "idx")
+    B, T = frames.shape[0], frames.shape[1]
+    K = idx.shape[-1]
+    row = frames[0, 0].numel() if T > 0 else 0
+    out = torch.empty((B, K) + tuple(frames.shape[2:]), dtype=torch.float32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _capi.check(_capi.lib().sasvqa_gather_frames_f32(frames.data_ptr(), idx.data_ptr(), B, T, K, row,
+                                                         out.data_ptr(), _stream(frames)), "sasvqa_gather_frames_f32")
+    return out
+
+
+# ---- whole path
+def mdf_sample_device(enc: FrameEncoder, clips: torch.Tensor, K: int, W: int, want_frames: bool = True,
+                      want_aux: bool = False) -> dict:
+    """clips: [B, T, 224, 224, 3] uint8 or [B, T, 3, 224, 224] fp32, on the GPU."""
+    if not clips.is_cuda:
+        raise _capi.SasvqaError("clips must be a CUDA tensor (use mdf_sample_host for host buffers)")
+    clips = clips.contiguous()
+    B, T = clips.shape[0], clips.shape[1]
+    dev = clips.device
+    idx = torch.empty(B, K, dtype=torch.int32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    lcl = torch.empty(B, T, dtype=torch.float32, device=dev) if want_aux else None
+    feats = torch.empty(B, T, HIDDEN, dtype=torch.float32, device=dev) if want_aux else None
+    sampled = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, device=dev) if want_frames else None
+    if clips.dtype == torch.uint8:
+        fn, name = _capi.lib().sasvqa_mdf_sample_u8, "sasvqa_mdf_sample_u8"
+    elif clips.dtype == torch.float32:
+        fn, name = _capi.lib().sasvqa_mdf_sample_f32, "sasvqa_mdf_sample_f32"
+    else:
+        raise TypeError(f"clips must be uint8 HWC or float32 CHW, got {clips.dtype}")
+    with torch.cuda.device(dev):
+        _capi.check(fn(enc.handle, clips.data_ptr(), B, T, int(K), int(W), idx.data_ptr(), status.data_ptr(),
+                       _capi.ptr(lcl), _capi.ptr(feats), _capi.ptr(sampled), _stream(clips)), name)
+    return dict(indices=idx, status=status, lcl_avg=lcl, feats=feats, frames=sampled)
+
+
+def mdf_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, K: int, W: int, idx_out: torch.Tensor = None,
+                    status_out: torch.Tensor = None, frames_out: torch.Tensor = None, want_frames: bool = True) -> dict:
+    """clips_host: [B, T, 224, 224, 3] uint8 in (ideally pinned) host memory.  Results land in host tensors."""
+    if clips_host.is_cuda or clips_host.dtype != torch.uint8:
+        raise TypeError("clips_host must be a uint8 CPU tensor")
+    clips_host = clips_host.contiguous()
+    B, T = clips_host.shape[0], clips_host.shape[1]
+    pin = torch.cuda.is_available()
+    if idx_out is None:
+        idx_out = torch.empty(B, K, dtype=torch.int32, pin_memory=pin)
+    if status_out is None:
+        status_out = torch.empty(B, dtype=torch.int32, pin_memory=pin)
+    if frames_out is None and want_frames:
+        frames_out = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, pin_memory=pin)
+    with torch.cuda.device(enc.device):
+        _capi.check(_capi.lib().sasvqa_mdf_sample_host(enc.handle, clips_host.data_ptr(), B, T, int(K), int(W),
+                                                       idx_out.data_ptr(), status_out.data_ptr(),
+                                                       _capi.ptr(frames_out) if want_frames else None),
+                    "sasvqa_mdf_sample_host")
+    return dict(indices=idx_out, status=status_out, frames=frames_out if want_frames else None)
+
+
+def launch_count() -> int:
+    return int(_capi.lib().sasvqa_launch_count())
+
+
+# ---- test hooks
+def test_gemm(a: torch.Tensor, b: torch.Tensor, mode: int, vec: torch.Tensor, out_f32: torch.Tensor = None,
+              use_simt: bool = False):
+    a = _need_cuda(a, torch.bfloat16, "a")
+    b = _need_cuda(b, torch.bfloat16, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    out_bf16 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if mode in (0, 1) else None
+    with torch.cuda.device(a.device):
+        _capi.check(_capi.lib().sasvqa_test_gemm(a.data_ptr(), b.data_ptr(), M, N, K, mode, vec.data_ptr(),
+                                                 _capi.ptr(out_bf16), _capi.ptr(out_f32), int(use_simt), _stream(a)),
+                    "sasvqa_test_gemm")
+    return out_bf16 if mode in (0, 1) else out_f32
+
+
+def test_attention(qkv: torch.Tensor) -> torch.Tensor:
+    qkv = _need_cuda(qkv, torch.bfloat16, "qkv")
+    n = qkv.shape[0] // TOKENS
+    out = torch.empty(n * TOKENS, HIDDEN, dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        _capi.check(_capi.lib().sasvqa_test_attention(qkv.data_ptr(), n, out.data_ptr(), _stream(qkv)),
+                    "sasvqa_test_attention")
+    return out
+
+
+def test_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
+    x = _need_cuda(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().sasvqa_test_layernorm(x.data_ptr(), x.shape[0], gamma.data_ptr(), beta.data_ptr(),
+                                                      out.data_ptr(), _stream(x)), "sasvqa_test_layernorm")
+    return out

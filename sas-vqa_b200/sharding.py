@@ -1,0 +1,58 @@
+"""Multi-GPU layer: videos are independent (the reference loop extract_features.py:80-97 keeps
+no state between iterations), so the clip list is sharded by rank -- one process per GPU -- and
+the only collective is an all-gather of the per-video index lists at the end.  The reference's
+own scheme (intra-video DataParallel over 4 GPUs, extract_features.py:48) is not reproduced.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous balanced slice [start, end) of ``n_items`` owned by ``rank`` (sizes differ by <= 1)."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks (sharded with ``shard_range``) into the full [n_total, ...]
+    tensor on every rank.  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    if not dist.is_available() or not dist.is_initialized():
+        assert local.shape[0] == n_total
+        return local
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    max_rows = (n_total + world - 1) // world
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    rows = []
+    for r, part in enumerate(parts):
+        s, e = shard_range(n_total, r, world)
+        rows.append(part[: e - s])
+    return torch.cat(rows, dim=0)
+
+
+def sample_mdf_sharded(make_local_clips, n_clips: int, model, K: int, W: int, group=None, sampler=None) -> dict:
+    """Each rank samples its shard of the clip list and all ranks end with the full index table.
+
+    make_local_clips(start, end) -> clips tensor for global clip ids [start, end) (device-resident
+    uint8 [n, T, 224, 224, 3] or host tensor).  ``sampler`` defaults to sample_mdf_batch /
+    sample_mdf_host by residency.  Returns dict(indices [n_clips, K], status [n_clips], local=...)."""
+    from . import sampler as S
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    start, end = shard_range(n_clips, rank, world)
+    clips = make_local_clips(start, end)
+    if sampler is None:
+        sampler = S.sample_mdf_batch if clips.is_cuda else S.sample_mdf_host
+    local = sampler(clips, model, K, W)
+    idx, status = local["indices"], local["status"]
+    if dist.is_initialized() and world > 1 and dist.get_backend(group) == "nccl" and not idx.is_cuda:
+        idx, status = idx.cuda(), status.cuda()
+    return dict(indices=all_gather_rows(idx, n_clips, group), status=all_gather_rows(status, n_clips, group),
+                local=local, shard=(start, end))

@@ -1,0 +1,168 @@
+"""CPU-side checks (run with -m "not gpu"): the C-ABI library loads and exports every symbol
+the header declares, host logic matches the oracle, on-disk formats round-trip, the product
+never touches oracle/, and the N>1 path works over gloo with world_size 2."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import sasvqa_b200
+from sasvqa_b200 import _capi, ops, sampler, sharding, synth, writer
+from oracle import mdf
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sasvqa.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sasvqa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sasvqa.h but not exported"
+    assert set(syms) == set(_capi.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _capi.lib().sasvqa_abi_version() == 1
+
+
+def test_library_is_sm100a_blackwell_native():
+    sass = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass.stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):      # tcgen05.mma, TMA load, tcgen05.ld
+        assert mnemonic in sass.stdout, mnemonic
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    pkg = os.path.join(ROOT, "sas-vqa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+    with pytest.raises(_capi.SasvqaError):
+        ops.preprocess_u8(torch.zeros(1, 224, 224, 3, dtype=torch.uint8))        # CPU tensor -> loud failure
+    with pytest.raises(_capi.SasvqaError):
+        ops.mdf_scores(torch.zeros(4, 768), 1)
+
+
+def test_uniform_and_git6_index_math_match_oracle():
+    for T in (8, 17, 64, 100, 333):
+        for K in (1, 3, 8, 16):
+            if K <= T:
+                assert sampler.uniform_indices(T, K) == mdf.uniform_indices(T, K)
+                fr = torch.arange(T).float().view(T, 1)
+                assert sampler.sample_frames_uniform(fr, K).view(-1).long().tolist() == mdf.uniform_indices(T, K)
+    np.random.seed(666)
+    got = [sampler.sample_frame_indices(np.arange(T), 6, 4, T).tolist() for T in (40, 64, 300)]
+    rng = np.random.RandomState(666)
+    want = [mdf.git6_indices(T, 6, 4, rng=rng).tolist() for T in (40, 64, 300)]
+    assert got == want
+
+
+def test_empty_clip_contract():
+    dc = {"Failure": 0, "Zeros": 0}
+    sd = {}
+
+    class Dummy(ops.FrameEncoder):      # no GPU needed: T == 0 never reaches the encoder
+        def __init__(self):
+            self._h = None
+            self.device = torch.device("cpu")
+
+    out = sampler.sample_representative_frames(torch.zeros(0, 3, 224, 224), Dummy(), 16, 8, dc)
+    assert tuple(out.shape) == (16, 3, 224, 224) and float(out.abs().sum()) == 0 and dc["Zeros"] == 1
+    with pytest.raises(TypeError):      # the reference dereferences debug_counter unconditionally here
+        sampler.sample_representative_frames(torch.zeros(0, 3, 224, 224), Dummy(), 16, 8, None)
+
+
+def test_state_dict_flattening():
+    keys = synth.state_dict_keys()
+    assert len(keys) == 199 - 0 - 0 or len(keys) == 5 + 12 * 16 + 2
+    assert sum(int(np.prod(s)) for _, s in keys) == ops.NUM_PARAMS
+    sd = {k: torch.full(s, float(i)) for i, (k, s) in enumerate(keys)}
+    flat = ops.flatten_state_dict(sd)
+    assert flat.numel() == ops.NUM_PARAMS and float(flat[0]) == 0.0 and float(flat[-1]) == len(keys) - 1
+    bad = dict(sd)
+    bad.pop(keys[7][0])
+    with pytest.raises(KeyError):
+        ops.flatten_state_dict(bad)
+
+
+def test_hf_state_dict_key_order_matches():
+    tr = pytest.importorskip("transformers")
+    model = tr.GitVisionModel(tr.GitVisionConfig())
+    hf_keys = [k for k in model.state_dict().keys() if "position_ids" not in k]
+    assert hf_keys == [k for k, _ in synth.state_dict_keys()]
+
+
+def test_writers_round_trip(tmp_path):
+    mapping = writer.generate_vidid_json(["/d/video/vid12.avi", "/d/video/abc.mp4"], str(tmp_path / "vidmapping.json"))
+    assert mapping == {"vid12": 0, "abc": 1} == json.load(open(tmp_path / "vidmapping.json"))
+    K, img = 4, 8
+    frames = torch.randn(2, K, 3, img, img)
+    with writer.SampledFramesWriter(str(tmp_path / "msvd_qa_video_feat.h5"), 2, K, img=img, backend="npy") as w:
+        w[0] = frames[0]
+        w[1] = frames[1]
+    ds = writer.open_sampled_frames(str(tmp_path / "msvd_qa_video_feat.h5"))
+    assert ds.shape == (2, K, 3 * img * img) and ds.dtype == np.float32
+    # consumer-side view (src/datasets/dataset_video_qa.py:53-56 + collator reshape)
+    assert np.array_equal(np.asarray(ds[1]).reshape(K, 3, img, img), frames[1].numpy())
+    qa = [{"question": "what", "video": 3, "answer": "x"}]
+    out = writer.write_sampled_inds(qa, [[5, 1, 9]], str(tmp_path / "qa_winds_val.json"))
+    assert json.load(open(tmp_path / "qa_winds_val.json")) == out and out[0]["sampled_inds"] == [5, 1, 9]
+    rec = writer.write_mdf_inds(mapping, torch.tensor([[1, 2], [3, 4]]), str(tmp_path / "mdf_inds.json"))
+    assert rec == {"vid12": [1, 2], "abc": [3, 4]}
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 256, 10000):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SASVQA_ROOT"])
+from sasvqa_b200 import sharding
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+n, K = 7, 4
+def make(s, e):
+    return torch.arange(s, e, dtype=torch.uint8).view(-1, 1)          # stand-in "clips": carry their id
+def fake_sampler(clips, model, K_, W_):                                 # deterministic per clip id
+    ids = clips.view(-1).to(torch.int32)
+    return dict(indices=ids[:, None] * 10 + torch.arange(K_, dtype=torch.int32)[None], status=ids % 2)
+res = sharding.sample_mdf_sharded(make, n, None, K, 8, sampler=fake_sampler)
+want = torch.arange(n, dtype=torch.int32)[:, None] * 10 + torch.arange(K, dtype=torch.int32)[None]
+assert torch.equal(res["indices"], want), res["indices"]
+assert torch.equal(res["status"], torch.arange(n, dtype=torch.int32) % 2)
+assert res["shard"] == sharding.shard_range(n, rank, world)
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_sharded_all_gather_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, SASVQA_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29653", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in o, o
