@@ -1,0 +1,336 @@
+"""bench.py -- sampled videos/sec of the MDF frame-sampling hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path over one batch of synthetic clips:
+uint8 decoded frames -> preprocess/patchify -> ViT-B/16 encoder -> pool + L2 norm -> windowed
+cosine scores -> greedy selection / top-K fallback -> gather of the K sampled frames.
+Workload at every N: BASELINE.json configs[1] per GPU (256 clips x 128 frames, K=16, W=8, bf16
+encoder); ranks own disjoint clip ids (weak scaling) and all-gather the index table each step.
+
+`value`  : device-resident inputs (clips already in HBM), CUDA-event timed, max over ranks.
+`e2e`    : the same step through the host-buffer C-ABI call (sasvqa_mdf_sample_host): pinned host
+           clips in, indices + sampled frames back in host memory, copies inside the timed region.
+`roofline`: the dominant kernel (tcgen05 encoder GEMM), timed live with CUDA events on its stream.
+`cpu_baseline` / `--impl reference`: the reference's CPU path (HF GitVisionModel fp32 + the oracle
+           restatement of its sampler, proven identical in tests/) on the box's host cores, on a
+           bounded sample (one clip of the same shape per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sampled videos/sec"
+UNIT = "videos/s"
+GEMM_FLOP_PER_FRAME = 2 * 196 * 768 * 768 + 12 * (2 * 197 * 768 * (2304 + 768 + 3072 + 3072))   # 33.70 GFLOP
+TOTAL_FLOP_PER_FRAME = GEMM_FLOP_PER_FRAME + 12 * (2 * 2 * 197 * 197 * 768)                       # 35.13 GFLOP
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=256, help="clips per GPU per step")
+    ap.add_argument("--frames", type=int, default=128, help="frames per clip (T)")
+    ap.add_argument("--K", type=int, default=16)
+    ap.add_argument("--W", type=int, default=8)
+    ap.add_argument("--chunk-frames", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=1, help="clips in the CPU baseline sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:  # noqa: BLE001
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_setup():
+    """The reference's CPU path: HF GitVisionModel (fp32, the third-party encoder it loads) driven
+    by the restated sampler (oracle/mdf.py == src/preprocessing/datautils/utils.py:31-94, proven by
+    tests/test_oracle_golden.py).  /root/reference itself does not exist on the GPU box."""
+    import torch
+    from oracle import mdf, vit
+    from sasvqa_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.random_encoder_state_dict(synth.REF_SEED)
+    try:
+        model = vit.hf_model_from_state_dict(sd)
+        enc_name = "HF GitVisionModel fp32"
+    except Exception:  # noqa: BLE001  (transformers missing)
+        model = vit.VitOracle(sd)
+        enc_name = "oracle ViT restatement fp32"
+    return mdf, vit, synth, model, enc_name
+
+
+def cpu_reference_time(args, n_clips: int, repeats: int, warm: int):
+    """Seconds per clip (best of `repeats`) for the reference CPU sampler on `n_clips` clips/step."""
+    import torch
+    mdf, vit, synth, model, enc_name = cpu_reference_setup()
+    clips = [vit.image_processor_224(synth.make_clip(cid, args.frames)) for cid in range(n_clips)]
+    times, picks = [], None
+    with torch.no_grad():
+        for it in range(warm + repeats):
+            t0 = time.perf_counter()
+            for fr in clips:
+                _, aux = mdf.sample_representative_frames(fr, model, args.K, args.W, {"Failure": 0, "Zeros": 0},
+                                                          return_aux=True)
+            dt = time.perf_counter() - t0
+            if it >= warm:
+                times.append(dt)
+            picks = aux["indices"]
+    return times, enc_name, torch.get_num_threads(), picks
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, enc_name, threads, _ = cpu_reference_time(args, args.cpu_clips, max(1, args.steps), max(0, min(args.warmup, 1)))
+    per_step = sum(times) / len(times)
+    value = args.cpu_clips / per_step
+    sample = (f"{args.cpu_clips} clip(s) x {args.frames} frames per step (bounded sample of the {args.clips}-clip batch), "
+              f"{enc_name} + restated sampler, torch.no_grad, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": max(0, min(args.warmup, 1)), "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "frames_per_s": value * args.frames,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"MDF batch of {args.clips} synthetic {args.frames}-frame 224x224 clips per GPU, K={args.K}, W={args.W} "
+                    f"(BASELINE configs[1]), random-init ViT-B/16 encoder",
+        "clips_per_gpu": args.clips, "frames_per_clip": args.frames, "K": args.K, "W": args.W,
+        "global_clips": args.clips * n_gpus, "parallelism": f"dp{n_gpus} (clips sharded by rank)",
+        "l2": "inputs larger than L2 (4.9 GB uint8 per GPU streamed once per step)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sasvqa_b200 as sas
+    from sasvqa_b200 import ops, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the product has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    B, T, K, W = args.clips, args.frames, args.K, args.W
+    enc = sas.FrameEncoder(synth.random_encoder_state_dict(synth.REF_SEED), chunk_frames=args.chunk_frames)
+    n_total = B * world
+    start, end = sharding.shard_range(n_total, rank, world)
+    clips = synth.make_clips(range(start, end), T, device=dev)          # [B, T, 224, 224, 3] uint8, resident in HBM
+    torch.cuda.synchronize()
+
+    def step():
+        res = sas.sample_mdf_batch(clips, enc, K, W, want_frames=True)
+        table = sharding.all_gather_rows(res["indices"], n_total) if world > 1 else res["indices"]
+        return res, table
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res, table = step()
+    barrier()
+    launches0 = ops.launch_count()
+    enc.profile_enable(True)
+    sampler_thread = ClockSampler(physical_gpu_index(local_rank))
+    sampler_thread.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        res, table = step()
+    ev1.record()
+    barrier()
+    clocks = sampler_thread.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    prof = enc.profile_read()
+    enc.profile_enable(False)
+    launches = ops.launch_count() - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_total / (ms_per_step / 1e3)
+    status = res["status"].cpu()
+
+    # ---- roofline of the dominant kernel (all five GEMM shapes run the same tcgen05 kernel)
+    gemm_ms = sum(prof[k][0] for k in prof if k.startswith("gemm_"))
+    gemm_launches = sum(prof[k][1] for k in prof if k.startswith("gemm_"))
+    frames_timed = B * T * args.steps
+    achieved_tf = GEMM_FLOP_PER_FRAME * frames_timed / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    stage_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tf_sustained"],
+        "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+        "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+        "flop_per_launch": GEMM_FLOP_PER_FRAME * frames_timed / max(gemm_launches, 1),
+        "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches": gemm_launches,
+        "gemm_share_of_step": gemm_ms / max(sum(v[0] for v in prof.values()), 1e-9),
+        "whole_path_tflops": TOTAL_FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12,
+        "whole_path_frac_of_sustained": TOTAL_FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12 / peaks["tf_sustained"],
+        "stage_ms_per_step": stage_ms,
+    }
+
+    # ---- end to end through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        host_clips = torch.empty(clips.shape, dtype=torch.uint8, pin_memory=True)
+        host_clips.copy_(clips)
+        idx_h = torch.empty(B, K, dtype=torch.int32, pin_memory=True)
+        st_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        fr_h = torch.empty(B, K, 3, 224, 224, dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            out = sas.sample_mdf_host(host_clips, enc, K, W, idx_out=idx_h, status_out=st_h, frames_out=fr_h)
+            if world > 1:
+                sharding.all_gather_rows(out["indices"].to(dev), n_total)
+            return out
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out = e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_s = float(dt.item()) / args.e2e_steps
+        assert torch.equal(out["indices"], res["indices"].cpu()), "host path and device path disagree"
+        e2e = {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(host_clips.numel()),
+               "d2h_bytes_per_step": int(idx_h.numel() * 4 + st_h.numel() * 4 + fr_h.numel() * 4),
+               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
+               "api": "sasvqa_mdf_sample_host (pinned uint8 clips in; indices, status and sampled fp32 frames out)"}
+        del host_clips, fr_h
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference CPU sampler on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, enc_name, threads, picks = cpu_reference_time(args, args.cpu_clips, 1, 0)
+        cpu_v = args.cpu_clips / min(times)
+        gpu_picks = res["indices"][0].cpu().tolist() if start == 0 else None
+        cpu = {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_clips} clip(s) x {T} frames of the same workload (clip id 0), {enc_name} + restated "
+                         f"sampler, torch.no_grad, 1 timed pass",
+               "cpu_indices_clip0": picks, "gpu_indices_clip0": gpu_picks}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+            "frames_per_s": value * T, "clocks": clocks, "gpu_launches": int(launches),
+            "status_counts": {"greedy": int((status == 0).sum()), "fallback": int((status == 1).sum())},
+            "roofline": roofline,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
