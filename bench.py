@@ -136,11 +136,14 @@ def cpu_reference_setup():
     return mdf, vit, synth, model, enc_name
 
 
-def cpu_reference_time(args, n_clips: int, repeats: int, warm: int):
-    """Seconds per clip (best of `repeats`) for the reference CPU sampler on `n_clips` clips/step."""
+def cpu_reference_time(args, n_clips: int, repeats: int, warm: int, u8_clips=None):
+    """Per-step seconds for the reference CPU sampler on `n_clips` clips/step.  `u8_clips`: the
+    very clips the GPU arm sampled (uint8 [n, T, 224, 224, 3] on the host); else generated here."""
     import torch
     mdf, vit, synth, model, enc_name = cpu_reference_setup()
-    clips = [vit.image_processor_224(synth.make_clip(cid, args.frames)) for cid in range(n_clips)]
+    if u8_clips is None:
+        u8_clips = [synth.make_clip(cid, args.frames) for cid in range(n_clips)]
+    clips = [vit.image_processor_224(u8_clips[i]) for i in range(n_clips)]
     times, picks = [], None
     with torch.no_grad():
         for it in range(warm + repeats):
@@ -152,14 +155,15 @@ def cpu_reference_time(args, n_clips: int, repeats: int, warm: int):
             if it >= warm:
                 times.append(dt)
             picks = aux["indices"]
-    return times, enc_name, torch.get_num_threads(), picks
+    return times, enc_name, torch.get_num_threads(), picks, aux
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times, enc_name, threads, _ = cpu_reference_time(args, args.cpu_clips, max(1, args.steps), max(0, min(args.warmup, 1)))
+    times, enc_name, threads, _, _ = cpu_reference_time(args, args.cpu_clips, max(1, args.steps),
+                                                        max(0, min(args.warmup, 1)))
     per_step = sum(times) / len(times)
     value = args.cpu_clips / per_step
     sample = (f"{args.cpu_clips} clip(s) x {args.frames} frames per step (bounded sample of the {args.clips}-clip batch), "
@@ -301,13 +305,18 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only): the reference CPU sampler on a bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, enc_name, threads, picks = cpu_reference_time(args, args.cpu_clips, 1, 0)
-        cpu_v = args.cpu_clips / min(times)
-        gpu_picks = res["indices"][0].cpu().tolist() if start == 0 else None
+        nc = args.cpu_clips
+        times, enc_name, threads, picks, aux = cpu_reference_time(args, nc, 1, 0, u8_clips=clips[:nc].cpu())
+        cpu_v = nc / min(times)
+        gpu_picks = res["indices"][nc - 1].cpu().tolist()
+        # same clip, both arms: identical indices unless the deciding scores tie within the bf16-induced error
+        lcl_ref = aux["lcl_avg"]
+        gap = max([abs(float(lcl_ref[a]) - float(lcl_ref[b])) for a, b in zip(gpu_picks, picks) if a != b] or [0.0])
         cpu = {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_clips} clip(s) x {T} frames of the same workload (clip id 0), {enc_name} + restated "
-                         f"sampler, torch.no_grad, 1 timed pass",
-               "cpu_indices_clip0": picks, "gpu_indices_clip0": gpu_picks}
+               "sample": f"{nc} clip(s) x {T} frames: the first clip(s) of the GPU arm's own batch copied to the host, "
+                         f"{enc_name} + restated sampler, torch.no_grad, 1 timed pass",
+               "cpu_indices": picks, "gpu_indices": gpu_picks, "indices_identical": picks == gpu_picks,
+               "max_score_gap_where_different": gap}
 
     if rank == 0:
         line = {

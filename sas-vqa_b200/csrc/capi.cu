@@ -114,11 +114,15 @@ int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, 
     CUtensorMap ma, mb;
     int rc = make_tensor_map_bf16_kmajor(&ma, a, (uint64_t)M, (uint64_t)K, 128);
     if (rc) return rc;
-    if ((rc = make_tensor_map_bf16_kmajor(&mb, b, (uint64_t)N, (uint64_t)K, 256))) return rc;
+    if ((rc = make_tensor_map_bf16_kmajor(&mb, b, (uint64_t)N, (uint64_t)K, 128))) return rc;
+    CUtensorMap mo = ma;
+    if (mode == EPI_BIAS_BF16 || mode == EPI_BIAS_GELU_BF16) rc = make_tensor_map_out(&mo, out_bf16, (uint64_t)M, (uint64_t)N, 0);
+    else if (mode == EPI_BIAS_RESID_F32) rc = make_tensor_map_out(&mo, out_f32, (uint64_t)M, (uint64_t)N, 1);
+    if (rc) return rc;
     int dev = 0, sms = 148;
     SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
     SASVQA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return launch_gemm_tcgen05(g, &ma, &mb, sms, S(stream));
+    return launch_gemm_tcgen05(g, &ma, &mb, &mo, sms, S(stream));
 }
 int sasvqa_test_attention(const uint16_t* qkv, int n_frames, uint16_t* out, void* stream) {
     return launch_attention(CBF(qkv), BF(out), n_frames, S(stream));

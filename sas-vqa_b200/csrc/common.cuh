@@ -69,8 +69,9 @@ struct GemmArgs {
 };
 
 // launchers (each returns 0 or an error code, async on `stream`)
-int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUtensorMap* map_b, int num_sms,
-                        cudaStream_t stream);
+int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUtensorMap* map_b,
+                        const CUtensorMap* map_out, int num_sms, cudaStream_t stream);
+int make_tensor_map_out(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, int is_f32);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 

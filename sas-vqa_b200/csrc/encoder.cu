@@ -69,7 +69,8 @@ struct SasvqaEncoder {
     float* x = nullptr;               // [chunk*197, 768]  fp32 residual stream
     __nv_bfloat16* h = nullptr;       // [chunk*197, 768]  LN output / attention output
     __nv_bfloat16* big = nullptr;     // [chunk*197, 3072] qkv (as [.,2304]) / fc1 output / patch matrix (as [chunk*196,768])
-    CUtensorMap m_h, m_big_fc, m_big_patch;
+    CUtensorMap m_h, m_big_fc, m_big_patch;       // A-operand views
+    CUtensorMap m_out_qkv, m_out_fc1, m_out_x;    // TMA-store views of big ([.,2304] / [.,3072]) and x
     // scratch for the whole-path entry points (grown on demand)
     float* feats = nullptr;
     size_t feats_cap = 0;
@@ -124,10 +125,11 @@ struct Scope {
     }
 };
 
-int gemm(SasvqaEncoder* e, int kind, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, cudaStream_t s) {
+int gemm(SasvqaEncoder* e, int kind, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb,
+         const CUtensorMap* mo, cudaStream_t s) {
     Scope sc(e, kind, s);
     if (e->use_simt) return launch_gemm_simt(g, s);
-    return launch_gemm_tcgen05(g, ma, mb, e->num_sms, s);
+    return launch_gemm_tcgen05(g, ma, mb, mo, e->num_sms, s);
 }
 
 // encode `n` frames whose bf16 patch matrix is `patches` (map_patches describes it); leaves the
@@ -139,7 +141,7 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
     GemmArgs g{};
     g.A = patches; g.B = e->w_patch; g.M = n * kPatches; g.N = kHidden; g.K = kHidden;
     g.epilogue = EPI_PATCH_EMBED_F32; g.pos = e->pos; g.out_f32 = e->x;
-    if ((rc = gemm(e, PK_GEMM_PATCH, g, map_patches, &e->m_patch_w, s))) return rc;
+    if ((rc = gemm(e, PK_GEMM_PATCH, g, map_patches, &e->m_patch_w, nullptr, s))) return rc;
     {
         Scope sc(e, PK_PRE_LN, s);
         if ((rc = launch_pre_layernorm(e->x, n, e->cls_pos0, e->pre_g, e->pre_b, s))) return rc;
@@ -153,7 +155,7 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
         g = GemmArgs{};
         g.A = e->h; g.B = L.w_qkv; g.M = M; g.N = kQkv; g.K = kHidden;
         g.epilogue = EPI_BIAS_BF16; g.bias = L.b_qkv; g.out_bf16 = e->big;
-        if ((rc = gemm(e, PK_GEMM_QKV, g, &e->m_h, &L.m_qkv, s))) return rc;
+        if ((rc = gemm(e, PK_GEMM_QKV, g, &e->m_h, &L.m_qkv, &e->m_out_qkv, s))) return rc;
         {
             Scope sc(e, PK_ATTENTION, s);
             if ((rc = launch_attention(e->big, e->h, n, s))) return rc;
@@ -161,7 +163,7 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
         g = GemmArgs{};
         g.A = e->h; g.B = L.w_out; g.M = M; g.N = kHidden; g.K = kHidden;
         g.epilogue = EPI_BIAS_RESID_F32; g.bias = L.b_out; g.out_f32 = e->x;
-        if ((rc = gemm(e, PK_GEMM_OUT, g, &e->m_h, &L.m_out, s))) return rc;
+        if ((rc = gemm(e, PK_GEMM_OUT, g, &e->m_h, &L.m_out, &e->m_out_x, s))) return rc;
         {
             Scope sc(e, PK_LN, s);
             if ((rc = launch_layernorm_bf16(e->x, e->h, M, L.ln2_g, L.ln2_b, s))) return rc;
@@ -169,11 +171,11 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
         g = GemmArgs{};
         g.A = e->h; g.B = L.w_fc1; g.M = M; g.N = kFfn; g.K = kHidden;
         g.epilogue = EPI_BIAS_GELU_BF16; g.bias = L.b_fc1; g.out_bf16 = e->big;
-        if ((rc = gemm(e, PK_GEMM_FC1, g, &e->m_h, &L.m_fc1, s))) return rc;
+        if ((rc = gemm(e, PK_GEMM_FC1, g, &e->m_h, &L.m_fc1, &e->m_out_fc1, s))) return rc;
         g = GemmArgs{};
         g.A = e->big; g.B = L.w_fc2; g.M = M; g.N = kHidden; g.K = kFfn;
         g.epilogue = EPI_BIAS_RESID_F32; g.bias = L.b_fc2; g.out_f32 = e->x;
-        if ((rc = gemm(e, PK_GEMM_FC2, g, &e->m_big_fc, &L.m_fc2, s))) return rc;
+        if ((rc = gemm(e, PK_GEMM_FC2, g, &e->m_big_fc, &L.m_fc2, &e->m_out_x, s))) return rc;
     }
     return 0;
 }
@@ -295,16 +297,19 @@ int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames
     }
     TRYCUDA(cudaMemset(e->h, 0, rows * kHidden * sizeof(__nv_bfloat16)));
     TRYCUDA(cudaMemset(e->big, 0, rows * kFfn * sizeof(__nv_bfloat16)));
-    TRY(make_tensor_map_bf16_kmajor(&e->m_patch_w, e->w_patch, kHidden, kHidden, 256));
+    TRY(make_tensor_map_bf16_kmajor(&e->m_patch_w, e->w_patch, kHidden, kHidden, 128));
+    TRY(make_tensor_map_out(&e->m_out_qkv, e->big, rows, kQkv, 0));
+    TRY(make_tensor_map_out(&e->m_out_fc1, e->big, rows, kFfn, 0));
+    TRY(make_tensor_map_out(&e->m_out_x, e->x, rows, kHidden, 1));
     TRY(make_tensor_map_bf16_kmajor(&e->m_h, e->h, rows, kHidden, 128));
     TRY(make_tensor_map_bf16_kmajor(&e->m_big_fc, e->big, rows, kFfn, 128));
     TRY(make_tensor_map_bf16_kmajor(&e->m_big_patch, e->big, (uint64_t)chunk_frames * kPatches, kHidden, 128));
     for (int l = 0; l < kLayers; ++l) {
         Layer& L = e->L[l];
-        TRY(make_tensor_map_bf16_kmajor(&L.m_qkv, L.w_qkv, kQkv, kHidden, 256));
-        TRY(make_tensor_map_bf16_kmajor(&L.m_out, L.w_out, kHidden, kHidden, 256));
-        TRY(make_tensor_map_bf16_kmajor(&L.m_fc1, L.w_fc1, kFfn, kHidden, 256));
-        TRY(make_tensor_map_bf16_kmajor(&L.m_fc2, L.w_fc2, kHidden, kFfn, 256));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_qkv, L.w_qkv, kQkv, kHidden, 128));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_out, L.w_out, kHidden, kHidden, 128));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_fc1, L.w_fc1, kFfn, kHidden, 128));
+        TRY(make_tensor_map_bf16_kmajor(&L.m_fc2, L.w_fc2, kHidden, kFfn, 128));
     }
     TRYCUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));

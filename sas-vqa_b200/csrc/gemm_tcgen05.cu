@@ -1,51 +1,77 @@
 // Encoder GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (bf16 in, fp32 accumulate in TMEM)
-// with the encoder's epilogues fused (bias / quick_gelu / in-place fp32 residual / patch-embed
+// with the encoder's epilogues fused (bias / quick_gelu / fp32 residual add / patch-embed
 // scatter + position embedding).
 //
 // Replaces the cuBLAS/cuDNN calls behind the HF GitVisionTransformer the reference runs
 // (reference: src/preprocessing/datautils/utils.py:40 -> transformers modeling_git.py:596-666,
 // :461-467): q/k/v/out projections, fc1, fc2 and the patch-embedding convolution.
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0     : TMA producer  -- cp.async.bulk.tensor 2D loads of A (128x64) and B (256x64) bf16
-//                tiles, 128B-swizzled, into a 4-stage shared-memory ring (mbarrier full/empty)
-//   warp 1     : TMEM allocator + MMA issuer -- one lane issues tcgen05.mma.cta_group::1.kind::f16
-//                (M=128, N=256, K=16) x4 per stage; tcgen05.commit frees the stage / publishes
-//                the accumulator
-//   warps 2..5 : epilogue -- tcgen05.ld 32x32b.x32 of the fp32 accumulator (2 x 256 TMEM columns,
-//                double buffered so the epilogue of tile i overlaps the MMAs of tile i+1),
-//                fused elementwise work, vectorised global stores
+// Structure: persistent, warp-specialised, one CTA per SM, CTA PAIRS (cluster 2x1x1) driving
+// tcgen05.mma.cta_group::2 -- UMMA tile 256 (M, 128 rows per CTA) x 256 (N) x 16 (K).  Each CTA
+// stages its own 128 A rows and HALF of the B tile (128 of the 256 weight rows), so per 64-wide
+// K block a CTA pulls 32 KiB from L2 instead of 48 KiB (the v1 single-CTA kernel was L2->SMEM
+// bandwidth bound, see profiles/r01).
+//   warp 0     : TMA producer (both CTAs) -- cp.async.bulk.tensor.2d.cta_group::2 loads, 128B
+//                swizzle, 6-stage ring; all transaction bytes land on the LEADER CTA's mbarrier
+//   warp 1     : TMEM allocator (both CTAs); in the leader CTA one lane issues the MMAs and
+//                tcgen05.commit-multicasts "stage free" / "accumulator full" to both CTAs
+//   warps 2..5 : epilogue (both CTAs, 128 accumulator rows each): tcgen05.ld -> registers ->
+//                fused elementwise -> 128B-swizzled smem staging -> TMA store (bf16 outputs) or
+//                TMA reduce-add (fp32 residual stream, performed in L2: x is never read by the
+//                SM); accumulators are double buffered (2 x 256 TMEM columns) so the epilogue of
+//                tile i overlaps the MMAs of tile i+1
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sasvqa {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int BLOCK_M = 128;          // accumulator rows per CTA
+constexpr int PAIR_M = 256;           // rows per CTA pair = UMMA M
+constexpr int BLOCK_N = 256;          // UMMA N
+constexpr int HALF_N = 128;           // weight rows staged per CTA
+constexpr int BLOCK_K = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KiB
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;          // 512
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KiB
+constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;      // 16 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int NUM_THREADS = 192;
 constexpr int NUM_EPI_WARPS = 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_BUF_BYTES = 32 * 128;                  // 32 rows x 128 B, one TMA store box
+constexpr int EPI_BUFS_PER_WARP = 2;
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS_PER_WARP * EPI_BUF_BYTES;   // 32 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -71,37 +97,60 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+// 2-CTA TMA load: destination is this CTA's smem, completion bytes go to `bar_cluster` (the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                                uint32_t bar_cluster) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-__device__ __forceinline__ void tcgen05_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+__device__ __forceinline__ void tcgen05_alloc_cg2(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
                  : "memory");
 }
-__device__ __forceinline__ void tcgen05_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tcgen05_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+__device__ __forceinline__ void tcgen05_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrive (once) on the barrier at this smem offset in every CTA of `cta_mask` when all prior MMAs retire
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(cta_mask)
+        : "memory");
 }
-__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
+__device__ __forceinline__ void tcgen05_mma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                     uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -118,6 +167,9 @@ __device__ __forceinline__ void tcgen05_ld32(uint32_t taddr, uint32_t (&r)[32]) 
         : "memory");
 }
 __device__ __forceinline__ void tcgen05_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand, 128B swizzle (PTX ISA "tcgen05 matrix
 // descriptor"): start>>4 @[0,14), LBO>>4 @[16,30) (unused for one swizzle atom along K),
@@ -132,88 +184,129 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 }
 
 // Instruction descriptor for kind::f16: D=f32 (1@[4,6)), A=B=bf16 (1@[7,10), 1@[10,13)), both K-major,
-// N>>3 @[17,23), M>>4 @[24,29).
+// N>>3 @[17,23), M>>4 @[24,29).  M is the PAIR's 256 rows.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                            ((uint32_t)(BLOCK_M >> 4) << 24);
+                            ((uint32_t)(PAIR_M >> 4) << 24);
+
+// quick_gelu(x) = x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)); one MUFU op (tanh.approx, abs err
+// ~2^-11, far below the bf16 rounding of the output)
+__device__ __forceinline__ float quick_gelu_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
 
 // ---------------------------------------------------------------- epilogue
 struct EpiParams {
     int M, N;
-    int mode;
     const float* bias;
     const float* pos;
-    __nv_bfloat16* out_bf16;
-    float* out_f32;
+    float* out_f32;       // EPI_PATCH_EMBED_F32 only (direct stores with the frame/token row remap)
 };
 
-// One thread owns one accumulator row; `v` holds 32 consecutive columns starting at `col`.
-__device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int col, uint32_t (&v)[32]) {
+// staging layout == what a SWIZZLE_128B TMA box of 32 rows x 128 B expects (buffer 1024B-aligned)
+__device__ __forceinline__ uint32_t stage_addr(uint32_t buf, int row, int chunk16) {
+    return buf + (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4));
+}
+
+// bf16 outputs: 64 accumulator columns [col, col+64) of this warp's 32 rows -> one TMA store
+template <int MODE>
+__device__ __forceinline__ void epilogue_bf16_chunk(const EpiParams& p, const CUtensorMap* map_out, uint32_t taddr,
+                                                    uint32_t buf, int row0, int col, int lane) {
+    uint32_t v0[32], v1[32];
+    tcgen05_ld32(taddr, v0);
+    tcgen05_ld32(taddr + 32u, v1);
+    tcgen05_wait_ld();
+    uint32_t packed[32];
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const float4 b = __ldg(b4 + q);
+        const uint32_t* v = q < 8 ? v0 : v1;
+        const int o = (q & 7) * 4;
+        float f0 = __uint_as_float(v[o + 0]) + b.x, f1 = __uint_as_float(v[o + 1]) + b.y;
+        float f2 = __uint_as_float(v[o + 2]) + b.z, f3 = __uint_as_float(v[o + 3]) + b.w;
+        if (MODE == EPI_BIAS_GELU_BF16) {
+            f0 = quick_gelu_fast(f0);
+            f1 = quick_gelu_fast(f1);
+            f2 = quick_gelu_fast(f2);
+            f3 = quick_gelu_fast(f3);
+        }
+        packed[2 * q] = pack_bf16x2(f0, f1);
+        packed[2 * q + 1] = pack_bf16x2(f2, f3);
+    }
+    // the TMA store issued two chunks ago read this buffer; make sure it is done with it
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        st_shared_v4(stage_addr(buf, lane, j), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_out, buf, col, row0);
+        bulk_commit();
+    }
+}
+
+// fp32 residual stream: 32 accumulator columns -> x[row, col..col+32) += acc + bias, added in L2 by TMA
+__device__ __forceinline__ void epilogue_resid_chunk(const EpiParams& p, const CUtensorMap* map_out, uint32_t taddr,
+                                                     uint32_t buf, int row0, int col, int lane) {
+    uint32_t v[32];
+    tcgen05_ld32(taddr, v);
+    tcgen05_wait_ld();
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        st_shared_v4(stage_addr(buf, lane, j), __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x),
+                     __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y),
+                     __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z),
+                     __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_reduce_add_2d(map_out, buf, col, row0);
+        bulk_commit();
+    }
+}
+
+// patch embedding: x[frame*197 + 1 + patch, col..col+32) = acc + pos[1 + patch]  (rows are remapped per
+// frame, so this one writes straight from registers; it is 0.7 % of the encoder's FLOPs)
+__device__ __forceinline__ void epilogue_patch_chunk(const EpiParams& p, uint32_t taddr, int row, int col) {
+    uint32_t v[32];
+    tcgen05_ld32(taddr, v);
+    tcgen05_wait_ld();
     if (row >= p.M) return;
-    if (p.mode == EPI_BIAS_BF16 || p.mode == EPI_BIAS_GELU_BF16) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-        uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + (size_t)row * p.N + col);
+    const int frame = row / kPatches, patch = row - frame * kPatches;
+    const float4* p4 = reinterpret_cast<const float4*>(p.pos + (size_t)(1 + patch) * p.N + col);
+    float4* x4 = reinterpret_cast<float4*>(p.out_f32 + ((size_t)frame * kTokens + 1 + patch) * p.N + col);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float f[8];
-            float4 b0 = __ldg(b4 + 2 * q), b1 = __ldg(b4 + 2 * q + 1);
-            f[0] = __uint_as_float(v[8 * q + 0]) + b0.x;
-            f[1] = __uint_as_float(v[8 * q + 1]) + b0.y;
-            f[2] = __uint_as_float(v[8 * q + 2]) + b0.z;
-            f[3] = __uint_as_float(v[8 * q + 3]) + b0.w;
-            f[4] = __uint_as_float(v[8 * q + 4]) + b1.x;
-            f[5] = __uint_as_float(v[8 * q + 5]) + b1.y;
-            f[6] = __uint_as_float(v[8 * q + 6]) + b1.z;
-            f[7] = __uint_as_float(v[8 * q + 7]) + b1.w;
-            if (p.mode == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
-            }
-            uint4 o;
-            o.x = pack_bf16x2(f[0], f[1]);
-            o.y = pack_bf16x2(f[2], f[3]);
-            o.z = pack_bf16x2(f[4], f[5]);
-            o.w = pack_bf16x2(f[6], f[7]);
-            dst[q] = o;
-        }
-    } else if (p.mode == EPI_BIAS_RESID_F32) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-        float4* x4 = reinterpret_cast<float4*>(p.out_f32 + (size_t)row * p.N + col);
-        float4 r[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) r[q] = x4[q];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float4 b = __ldg(b4 + q);
-            r[q].x += __uint_as_float(v[4 * q + 0]) + b.x;
-            r[q].y += __uint_as_float(v[4 * q + 1]) + b.y;
-            r[q].z += __uint_as_float(v[4 * q + 2]) + b.z;
-            r[q].w += __uint_as_float(v[4 * q + 3]) + b.w;
-            x4[q] = r[q];
-        }
-    } else {  // EPI_PATCH_EMBED_F32
-        const int frame = row / kPatches, patch = row - frame * kPatches;
-        const float4* p4 = reinterpret_cast<const float4*>(p.pos + (size_t)(1 + patch) * p.N + col);
-        float4* x4 = reinterpret_cast<float4*>(p.out_f32 + ((size_t)frame * kTokens + 1 + patch) * p.N + col);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float4 e = __ldg(p4 + q), o;
-            o.x = __uint_as_float(v[4 * q + 0]) + e.x;
-            o.y = __uint_as_float(v[4 * q + 1]) + e.y;
-            o.z = __uint_as_float(v[4 * q + 2]) + e.z;
-            o.w = __uint_as_float(v[4 * q + 3]) + e.w;
-            x4[q] = o;
-        }
+    for (int q = 0; q < 8; ++q) {
+        const float4 e = __ldg(p4 + q);
+        float4 o;
+        o.x = __uint_as_float(v[4 * q + 0]) + e.x;
+        o.y = __uint_as_float(v[4 * q + 1]) + e.y;
+        o.z = __uint_as_float(v[4 * q + 2]) + e.z;
+        o.w = __uint_as_float(v[4 * q + 3]) + e.w;
+        x4[q] = o;
     }
 }
 
 // ---------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, EpiParams epi,
-                    int K) {
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_out, EpiParams epi, int K) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B needs 1024B alignment
-    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base slot
+    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + EPI_BYTES;
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -223,7 +316,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (epi.M + BLOCK_M - 1) / BLOCK_M;
+    const uint32_t cta_rank = cluster_ctarank();
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int m_tiles = (epi.M + PAIR_M - 1) / PAIR_M;
     const int n_tiles = epi.N / BLOCK_N;
     const int total_tiles = m_tiles * n_tiles;
     const int k_blocks = K / BLOCK_K;
@@ -231,56 +326,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_a);
         prefetch_tensormap(&map_b);
+        if (MODE != EPI_PATCH_EMBED_F32) prefetch_tensormap(&map_out);
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(full_bar(s), 1);                  // leader's producer arrive (+ bytes of both CTAs)
+            mbar_init(empty_bar(s), 1);                 // one multicast tcgen05.commit
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
-            mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS);
+            mbar_init(tmem_full_bar(a), 1);             // one multicast tcgen05.commit
+            mbar_init(tmem_empty_bar(a), 2 * NUM_EPI_WARPS);   // epilogue warps of BOTH CTAs (leader's copy is used)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        tcgen05_alloc(tmem_slot, TMEM_COLS);
-        tcgen05_relinquish();
+        tcgen05_alloc_cg2(tmem_slot, TMEM_COLS);
+        tcgen05_relinquish_cg2();
     }
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                 // peer's barriers are initialised, TMEM is allocated
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
                 const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                const int a_row = m_blk * PAIR_M + (int)cta_rank * BLOCK_M;
+                const int b_row = n_blk * BLOCK_N + (int)cta_rank * HALF_N;
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+                    if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE_BYTES);
+                    const uint32_t leader_full = mapa_cluster(full_bar(s), 0);
                     const uint32_t a_dst = smem_base + s * STAGE_BYTES;
-                    tma_load_2d(a_dst, &map_a, kb * BLOCK_K, m_blk * BLOCK_M, full_bar(s));
-                    tma_load_2d(a_dst + A_STAGE_BYTES, &map_b, kb * BLOCK_K, n_blk * BLOCK_N, full_bar(s));
+                    tma_load_2d_cg2(a_dst, &map_a, kb * BLOCK_K, a_row, leader_full);
+                    tma_load_2d_cg2(a_dst + A_STAGE_BYTES, &map_b, kb * BLOCK_K, b_row, leader_full);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (cta_rank == 0 && lane == 0) {
             uint32_t it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+            for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++t) {
                 const int a = t & 1;
                 const uint32_t aph = (t >> 1) & 1u;
-                mbar_wait(tmem_empty_bar(a), aph ^ 1u);     // epilogue has drained this accumulator
+                mbar_wait(tmem_empty_bar(a), aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(a * BLOCK_N);
                 for (int kb = 0; kb < k_blocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(full_bar(s), ph);             // TMA bytes have landed
+                    mbar_wait(full_bar(s), ph);             // both CTAs' TMA bytes have landed
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_base + s * STAGE_BYTES;
                     const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
@@ -288,44 +387,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
-                        tcgen05_mma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
-                                         (kb | k) != 0 ? 1u : 0u);
+                        tcgen05_mma_bf16_cg2(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                             (kb | k) != 0 ? 1u : 0u);
                     }
-                    tcgen05_commit(empty_bar(s));           // stage reusable once these MMAs retire
+                    tcgen05_commit_mc(empty_bar(s), 0b11);  // stage reusable in both CTAs once these MMAs retire
                 }
-                tcgen05_commit(tmem_full_bar(a));           // accumulator complete -> epilogue
+                tcgen05_commit_mc(tmem_full_bar(a), 0b11);  // accumulator complete -> both epilogues
             }
         }
     } else {
-        // ===================== epilogue warps =====================
+        // ===================== epilogue warps (both CTAs) =====================
         const int lane_grp = warp & 3;                      // TMEM lane quarter this warp may access
-        uint32_t t = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t buf0 = epi_base + (uint32_t)((warp - 2) * EPI_BUFS_PER_WARP * EPI_BUF_BYTES);
+        uint32_t t = 0, chunk_ctr = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++t) {
             const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
             const int a = t & 1;
             const uint32_t aph = (t >> 1) & 1u;
             mbar_wait(tmem_full_bar(a), aph);
             tcgen05_fence_after();
-            const int row = m_blk * BLOCK_M + lane_grp * 32 + lane;
+            const int row0 = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + lane_grp * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N);
+            if (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t v[32];
-                tcgen05_ld32(taddr + (uint32_t)c, v);
-                tcgen05_wait_ld();
-                epilogue_store(epi, row, n_blk * BLOCK_N + c, v);
+                for (int c = 0; c < BLOCK_N; c += 64, ++chunk_ctr)
+                    epilogue_bf16_chunk<MODE>(epi, &map_out, taddr + (uint32_t)c,
+                                              buf0 + (chunk_ctr & 1u) * EPI_BUF_BYTES, row0, n_blk * BLOCK_N + c, lane);
+            } else if (MODE == EPI_BIAS_RESID_F32) {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32, ++chunk_ctr)
+                    epilogue_resid_chunk(epi, &map_out, taddr + (uint32_t)c, buf0 + (chunk_ctr & 1u) * EPI_BUF_BYTES,
+                                         row0, n_blk * BLOCK_N + c, lane);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32)
+                    epilogue_patch_chunk(epi, taddr + (uint32_t)c, row0 + lane, n_blk * BLOCK_N + c);
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+            if (lane == 0) mbar_arrive_cluster(mapa_cluster(tmem_empty_bar(a), 0));
         }
+        if (lane == 0) bulk_wait_read<0>();                 // staging smem must outlive the last TMA stores
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                     // nobody exits while its peer can still signal it
     if (warp == 1) {
         tcgen05_fence_after();
-        tcgen05_dealloc(tmem_base, TMEM_COLS);
+        tcgen05_dealloc_cg2(tmem_base, TMEM_COLS);
     }
 }
 
@@ -346,22 +455,18 @@ PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-}  // namespace
-
-// 2D bf16 tensor [rows, cols] row-major; box = 64 columns (128 B) x box_rows rows; 128B swizzle;
-// out-of-bounds rows read as zero.
-int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+int encode_2d(CUtensorMap* map, CUtensorMapDataType dt, int elt_bytes, const void* base, uint64_t rows, uint64_t cols,
+              uint32_t box_cols, uint32_t box_rows) {
     PFN_encodeTiled enc = get_encode_fn();
     SASVQA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-    SASVQA_REQUIRE(cols % BLOCK_K == 0, "GEMM K must be a multiple of 64");
     SASVQA_REQUIRE(((uintptr_t)base & 15) == 0, "tensor base must be 16-byte aligned");
+    SASVQA_REQUIRE(box_cols * elt_bytes == 128, "box must span exactly one 128-byte swizzle row");
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+    cuuint64_t strides[1] = {cols * (uint64_t)elt_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return 2;
@@ -369,25 +474,53 @@ int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t row
     return 0;
 }
 
-int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUtensorMap* map_b, int num_sms,
-                        cudaStream_t stream) {
-    SASVQA_REQUIRE(g.N % BLOCK_N == 0, "GEMM N must be a multiple of 256");
-    SASVQA_REQUIRE(g.K % BLOCK_K == 0 && g.K >= BLOCK_K, "GEMM K must be a positive multiple of 64");
-    SASVQA_REQUIRE(g.M > 0, "GEMM M must be positive");
+template <int MODE>
+int launch_mode(const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, const CUtensorMap* mo, int num_sms,
+                cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         SASVQA_CUDA_CHECK(
-            cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            cudaFuncSetAttribute(gemm_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    EpiParams epi{g.M, g.N, g.epilogue, g.bias, g.pos, g.out_bf16, g.out_f32};
-    const int m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
-    const int total = m_tiles * (g.N / BLOCK_N);
-    const int grid = total < num_sms ? total : num_sms;
-    gemm_tcgen05_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(*map_a, *map_b, epi, g.K);
+    EpiParams epi{g.M, g.N, g.bias, g.pos, g.out_f32};
+    const int total = ((g.M + PAIR_M - 1) / PAIR_M) * (g.N / BLOCK_N);
+    const int pairs = std::max(1, std::min(num_sms / 2, total));
+    gemm_tcgen05_kernel<MODE><<<2 * pairs, NUM_THREADS, SMEM_BYTES, stream>>>(*ma, *mb, *mo, epi, g.K);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;
+}
+
+}  // namespace
+
+// operand maps: bf16 [rows, cols] row-major, box = 64 columns (128 B) x 128 rows, 128B swizzle, OOB rows read 0
+int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    SASVQA_REQUIRE(cols % BLOCK_K == 0, "GEMM K must be a multiple of 64");
+    return encode_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, BLOCK_K, box_rows);
+}
+
+// output maps for the TMA-store epilogues: box = 32 rows x 128 B (64 bf16 or 32 fp32 columns); rows past
+// `rows` are clipped by the hardware
+int make_tensor_map_out(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, int is_f32) {
+    if (is_f32) return encode_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, 32, 32);
+    return encode_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, 64, 32);
+}
+
+int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUtensorMap* map_b,
+                        const CUtensorMap* map_out, int num_sms, cudaStream_t stream) {
+    SASVQA_REQUIRE(g.N % BLOCK_N == 0, "GEMM N must be a multiple of 256");
+    SASVQA_REQUIRE(g.K % BLOCK_K == 0 && g.K >= BLOCK_K, "GEMM K must be a positive multiple of 64");
+    SASVQA_REQUIRE(g.M > 0, "GEMM M must be positive");
+    switch (g.epilogue) {
+        case EPI_BIAS_BF16: return launch_mode<EPI_BIAS_BF16>(g, map_a, map_b, map_out, num_sms, stream);
+        case EPI_BIAS_GELU_BF16: return launch_mode<EPI_BIAS_GELU_BF16>(g, map_a, map_b, map_out, num_sms, stream);
+        case EPI_BIAS_RESID_F32: return launch_mode<EPI_BIAS_RESID_F32>(g, map_a, map_b, map_out, num_sms, stream);
+        case EPI_PATCH_EMBED_F32: return launch_mode<EPI_PATCH_EMBED_F32>(g, map_a, map_b, map_a, num_sms, stream);
+        default: break;
+    }
+    SASVQA_REQUIRE(false, "unknown GEMM epilogue");
+    return 1;
 }
 
 }  // namespace sasvqa
