@@ -127,7 +127,8 @@ int sasvqa_profile_read(SasvqaEncoder* enc, double* ms_out, int64_t* scopes_out,
 int sasvqa_test_gemm(const uint16_t* a_bf16_dev, const uint16_t* b_bf16_dev, int M, int N, int K, int mode,
                      const float* bias_or_pos_dev, uint16_t* out_bf16_dev, float* out_f32_dev, int use_simt,
                      void* stream);
-int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* out_bf16_dev, void* stream);
+/* impl: 0 = tcgen05 kernel (product path), 1 = mma.sync check kernel */
+int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* out_bf16_dev, int impl, void* stream);
 int sasvqa_test_layernorm(const float* x_dev, int rows, const float* gamma_dev, const float* beta_dev,
                           uint16_t* out_bf16_dev, void* stream);
 

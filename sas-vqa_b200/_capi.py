@@ -36,7 +36,7 @@ SIGNATURES = {
     "sasvqa_profile_enable": (c_int, [_p, c_int]),
     "sasvqa_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "sasvqa_test_gemm": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, c_int, _p]),
-    "sasvqa_test_attention": (c_int, [_p, c_int, _p, _p]),
+    "sasvqa_test_attention": (c_int, [_p, c_int, _p, c_int, _p]),
     "sasvqa_test_layernorm": (c_int, [_p, c_int, _p, _p, _p, _p]),
 }
 

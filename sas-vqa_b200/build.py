@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsasvqa_b200.so")
-SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "attention.cu", "elementwise.cu", "select.cu"]
+SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "attention.cu", "attention_tcgen05.cu", "elementwise.cu", "select.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

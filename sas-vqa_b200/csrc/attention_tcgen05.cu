@@ -1,0 +1,370 @@
+// Per-frame multi-head self-attention of the ViT encoder on tcgen05 tensor cores (sm_100a):
+// 197 tokens, 12 heads x 64, softmax(Q K^T / 8) V with fp32 statistics (HF eager_attention_forward,
+// transformers modeling_git.py:556-575, reached from src/preprocessing/datautils/utils.py:40).
+//
+// Input  qkv [n*197, 2304] bf16 (q | k | v).   Output out [n*197, 768] bf16 (heads concatenated).
+//
+// Persistent CTAs, one work item = (frame, head).  Per item:
+//   warp 0      TMA: Q (2 x 128 rows), K, V (208 rows) -> 128B-swizzled smem, double buffered
+//   warp 1      MMA issuer: S_h = Q_h K^T  (M=128, N=208, K=64 -> 4 UMMAs, both operands K-major smem)
+//                           O_h = P_h V    (M=128, N=64, K=208 -> 13 UMMAs; A = P from TMEM, B = V as an
+//                                           MN-major smem operand, i.e. V exactly as TMA delivered it)
+//   warps 2-5   softmax + epilogue of query half h = 0 (rows 0..127), one thread per query row
+//   warps 6-9   same for half h = 1 (rows 128..196; rows >= 197 are skipped)
+// TMEM per half (256-column stride): S_h fp32 in columns [0,208); P_h = exp2(S - max) as packed bf16
+// overwrites columns [0,104) in place; O_h fp32 accumulates in columns [128,192).
+#include "common.cuh"
+
+namespace sasvqa {
+
+namespace {
+
+constexpr int KEYS = 208;                         // 197 keys padded to a multiple of 16
+constexpr int Q_HALF_BYTES = 128 * 128;           // 128 rows x 64 bf16
+constexpr int Q_BYTES = 2 * Q_HALF_BYTES;
+constexpr int KV_BYTES = KEYS * 128;              // 26 624
+constexpr int ITEM_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86 016 (multiple of 1024)
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_SMEM = 2 * ITEM_BYTES + 1024 + 256;
+constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            printf("sasvqa attention: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// smem operand descriptors, 128B swizzle, 1024 B between 8-row groups (see gemm_tcgen05.cu)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// S = Q K^T : M=128, N=208, A and B K-major, bf16 x bf16 -> f32
+constexpr uint32_t kIdescS = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KEYS >> 3) << 17) | ((128u >> 4) << 24);
+// O = P V   : M=128, N=64, A (TMEM) K-major, B MN-major (bit 16): V rows are keys with d contiguous
+constexpr uint32_t kIdescPV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                         __nv_bfloat16* __restrict__ out, int n_items) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + 2 * ITEM_BYTES;
+    auto kv_full = [&](int b) { return bar_base + 8u * b; };
+    auto kv_empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    auto s_full = [&](int h) { return bar_base + 8u * (4 + h); };
+    auto p_full = [&](int h) { return bar_base + 8u * (6 + h); };
+    auto o_full = [&](int h) { return bar_base + 8u * (8 + h); };
+    auto o_empty = [&](int h) { return bar_base + 8u * (10 + h); };
+    const uint32_t tmem_slot = bar_base + 8u * 12;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(kv_full(b), 1);
+            mbar_init(kv_empty(b), 1);
+            mbar_init(s_full(b), 1);
+            mbar_init(p_full(b), 128);
+            mbar_init(o_full(b), 1);
+            mbar_init(o_empty(b), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int b = it & 1;
+                const int frame = item / kHeads, head = item - frame * kHeads;
+                mbar_wait(kv_empty(b), ((it >> 1) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(kv_full(b), ITEM_BYTES);
+                const uint32_t dst = smem_base + b * ITEM_BYTES;
+                const int row = frame * kTokens;
+                tma_load_2d(dst, &map_q, head * kHeadDim, row, kv_full(b));
+                tma_load_2d(dst + Q_HALF_BYTES, &map_q, head * kHeadDim, row + 128, kv_full(b));
+                tma_load_2d(dst + Q_BYTES, &map_kv, kHidden + head * kHeadDim, row, kv_full(b));
+                tma_load_2d(dst + Q_BYTES + KV_BYTES, &map_kv, 2 * kHidden + head * kHeadDim, row, kv_full(b));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int b = it & 1;
+                const uint32_t par = it & 1u;
+                const uint32_t q_smem = smem_base + b * ITEM_BYTES;
+                const uint32_t k_smem = q_smem + Q_BYTES, v_smem = k_smem + KV_BYTES;
+                mbar_wait(kv_full(b), (it >> 1) & 1u);
+                tcgen05_fence_after();
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(o_empty(h), par ^ 1u);            // previous item's O_h (and P_h) fully consumed
+                    tcgen05_fence_after();
+                    const uint64_t adesc = desc_sw128(q_smem + h * Q_HALF_BYTES, 0);
+                    const uint64_t bdesc = desc_sw128(k_smem, 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_ss(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                               kIdescS, k != 0);
+                    tcgen05_commit(s_full(h));
+                }
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(p_full(h), par);                  // softmax wrote P_h into TMEM
+                    tcgen05_fence_after();
+                    const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
+#pragma unroll 1
+                    for (int k = 0; k < KEYS / 16; ++k)          // 16 keys = 8 packed-bf16 TMEM columns = 2048 B of V
+                        mma_ts(tmem_base + (uint32_t)(h * 256 + 128), tmem_base + (uint32_t)(h * 256 + 8 * k),
+                               vdesc + (uint64_t)(128 * k), kIdescPV, k != 0);
+                    tcgen05_commit(o_full(h));
+                }
+                tcgen05_commit(kv_empty(b));                    // Q/K/V smem of this item reusable
+            }
+        }
+    } else {
+        // ===================== softmax + epilogue: one thread per query row =====================
+        const int h = (warp - 2) >> 2;                          // query half
+        const int quarter = warp & 3;                           // TMEM lane quarter this warp may touch
+        const int qrow = h * 128 + quarter * 32 + lane;         // token index of this thread's query
+        const bool warp_active = (h * 128 + quarter * 32) < kTokens;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const int frame = item / kHeads, head = item - frame * kHeads;
+            mbar_wait(s_full(h), par);
+            tcgen05_fence_after();
+            float inv_l = 0.f;
+            if (warp_active) {
+                // ---- pass 1: row maximum over the 197 valid keys
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)(32 * c), v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
+                {
+                    uint32_t v[16];
+                    tmem_ld16(trow + 192u, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < kTokens - 192; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
+                const float m2 = mx * kScaleLog2e;
+                // ---- pass 2: P = exp2(S * scale - m2) -> packed bf16, in place over S; l = row sum
+                float l = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 6; ++c) {
+                    uint32_t v[32], pk[16];
+                    tmem_ld32(trow + (uint32_t)(32 * c), v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2));
+                        const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2));
+                        l += p0 + p1;
+                        pk[j] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st16(trow + (uint32_t)(16 * c), pk);
+                }
+                {
+                    uint32_t v[16], pk[8];
+                    tmem_ld16(trow + 192u, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float p0 = (2 * j < kTokens - 192) ? ex2(fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2)) : 0.f;
+                        const float p1 = (2 * j + 1 < kTokens - 192) ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2)) : 0.f;
+                        l += p0 + p1;
+                        pk[j] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st8(trow + 96u, pk);
+                }
+                tmem_wait_st();
+                inv_l = 1.0f / l;
+            }
+            tcgen05_fence_before();
+            mbar_arrive(p_full(h));
+            // ---- epilogue: O_h / l -> bf16 -> out[token, head*64 .. +64)
+            mbar_wait(o_full(h), par);
+            tcgen05_fence_after();
+            if (warp_active) {
+                uint32_t o0[32], o1[32];
+                tmem_ld32(trow + 128u, o0);
+                tmem_ld32(trow + 160u, o1);
+                tmem_wait_ld();
+                if (qrow < kTokens) {
+                    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + qrow) * kHidden + head * kHeadDim);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t* o = q < 4 ? o0 : o1;
+                        const int e = (q & 3) * 8;
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv_l, __uint_as_float(o[e + 1]) * inv_l);
+                        w.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l);
+                        w.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l);
+                        w.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l);
+                        dst[q] = w;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(o_empty(h));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+}  // namespace
+
+// qkv viewed as bf16 [rows, 2304]; boxes of 64 columns (one head of q, k or v) x 128 rows (Q) / 208 rows (K, V)
+int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, const void* qkv, uint64_t rows) {
+    int rc = make_tensor_map_bf16_kmajor(map_q, qkv, rows, kQkv, 128);
+    if (rc) return rc;
+    return make_tensor_map_bf16_kmajor(map_kv, qkv, rows, kQkv, KEYS);
+}
+
+int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int n_frames,
+                             int num_sms, cudaStream_t s) {
+    if (n_frames == 0) return 0;
+    SASVQA_REQUIRE(((uintptr_t)out & 15) == 0, "unaligned attention output");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SASVQA_CUDA_CHECK(
+            cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        attr_set = true;
+    }
+    const int n_items = n_frames * kHeads;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(*map_q, *map_kv, out, n_items);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace sasvqa

@@ -70,6 +70,8 @@ struct SasvqaEncoder {
     __nv_bfloat16* h = nullptr;       // [chunk*197, 768]  LN output / attention output
     __nv_bfloat16* big = nullptr;     // [chunk*197, 3072] qkv (as [.,2304]) / fc1 output / patch matrix (as [chunk*196,768])
     CUtensorMap m_h, m_big_fc, m_big_patch;       // A-operand views
+    CUtensorMap m_att_q, m_att_kv;                // attention operand views of big as [., 2304]
+    bool use_mma_attention = false;               // SASVQA_DEBUG_MMA_ATTENTION=1: legacy mma.sync kernel (bisecting aid)
     CUtensorMap m_out_qkv, m_out_fc1, m_out_x;    // TMA-store views of big ([.,2304] / [.,3072]) and x
     // scratch for the whole-path entry points (grown on demand)
     float* feats = nullptr;
@@ -158,7 +160,9 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
         if ((rc = gemm(e, PK_GEMM_QKV, g, &e->m_h, &L.m_qkv, &e->m_out_qkv, s))) return rc;
         {
             Scope sc(e, PK_ATTENTION, s);
-            if ((rc = launch_attention(e->big, e->h, n, s))) return rc;
+            if (e->use_mma_attention) rc = launch_attention(e->big, e->h, n, s);
+            else rc = launch_attention_tcgen05(&e->m_att_q, &e->m_att_kv, e->h, n, e->num_sms, s);
+            if (rc) return rc;
         }
         g = GemmArgs{};
         g.A = e->h; g.B = L.w_out; g.M = M; g.N = kHidden; g.K = kHidden;
@@ -212,6 +216,8 @@ int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames
     e->chunk_frames = chunk_frames;
     const char* dbg = getenv("SASVQA_DEBUG_SIMT_GEMM");
     e->use_simt = dbg != nullptr && dbg[0] == '1';
+    dbg = getenv("SASVQA_DEBUG_MMA_ATTENTION");
+    e->use_mma_attention = dbg != nullptr && dbg[0] == '1';
 
     // ---- upload the fp32 state dict once, carve bf16 matrices / fp32 vectors out of it on device
     float* raw = nullptr;
@@ -298,6 +304,7 @@ int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames
     TRYCUDA(cudaMemset(e->h, 0, rows * kHidden * sizeof(__nv_bfloat16)));
     TRYCUDA(cudaMemset(e->big, 0, rows * kFfn * sizeof(__nv_bfloat16)));
     TRY(make_tensor_map_bf16_kmajor(&e->m_patch_w, e->w_patch, kHidden, kHidden, 128));
+    TRY(make_attention_maps(&e->m_att_q, &e->m_att_kv, e->big, rows));
     TRY(make_tensor_map_out(&e->m_out_qkv, e->big, rows, kQkv, 0));
     TRY(make_tensor_map_out(&e->m_out_fc1, e->big, rows, kFfn, 0));
     TRY(make_tensor_map_out(&e->m_out_x, e->x, rows, kHidden, 1));

@@ -291,12 +291,12 @@ def test_gemm(a: torch.Tensor, b: torch.Tensor, mode: int, vec: torch.Tensor, ou
     return out_bf16 if mode in (0, 1) else out_f32
 
 
-def test_attention(qkv: torch.Tensor) -> torch.Tensor:
+def test_attention(qkv: torch.Tensor, impl: int = 0) -> torch.Tensor:
     qkv = _need_cuda(qkv, torch.bfloat16, "qkv")
     n = qkv.shape[0] // TOKENS
     out = torch.empty(n * TOKENS, HIDDEN, dtype=torch.bfloat16, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        _capi.check(_capi.lib().sasvqa_test_attention(qkv.data_ptr(), n, out.data_ptr(), _stream(qkv)),
+        _capi.check(_capi.lib().sasvqa_test_attention(qkv.data_ptr(), n, out.data_ptr(), int(impl), _stream(qkv)),
                     "sasvqa_test_attention")
     return out
 

@@ -122,11 +122,11 @@ def test_layernorm_vs_torch():
     assert (got - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-3
 
 
-def test_attention_vs_fp32_reference():
-    g = torch.Generator(device=DEV).manual_seed(2)
-    n = 3
+@pytest.mark.parametrize("impl,n", [(0, 3), (0, 40), (1, 3)], ids=["tcgen05", "tcgen05-persistent", "mma-check"])
+def test_attention_vs_fp32_reference(impl, n):
+    g = torch.Generator(device=DEV).manual_seed(2 + n)
     qkv = (torch.randn(n * 197, 2304, device=DEV, generator=g) * 1.5).to(torch.bfloat16)
-    got = ops.test_attention(qkv).float().view(n, 197, 12, 64)
+    got = ops.test_attention(qkv, impl=impl).float().view(n, 197, 12, 64)
     q, k, v = [t.view(n, 197, 12, 64).transpose(1, 2) for t in qkv.float().split(768, dim=1)]
     att = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1)
     want = (att @ v).transpose(1, 2)
