@@ -132,7 +132,7 @@ int sasvqa_test_attention(const uint16_t* qkv, int n_frames, uint16_t* out, int 
     int dev = 0, sms = 148;
     SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
     SASVQA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return launch_attention_tcgen05(&mq, &mkv, BF(out), n_frames, sms, S(stream));
+    return launch_attention_tcgen05(&mq, &mkv, BF(out), n_frames, sms, S(stream), impl >= 10 ? impl - 10 : 0);
 }
 int sasvqa_test_layernorm(const float* x, int rows, const float* gamma, const float* beta, uint16_t* out, void* stream) {
     return launch_layernorm_bf16(x, BF(out), rows, gamma, beta, S(stream));
