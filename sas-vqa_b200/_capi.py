@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint16, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsasvqa_b200.so")
+LIB_PATH = os.path.join(HERE, "libsasvqa_b200%s.so" % os.environ.get("SASVQA_LIB_SUFFIX", ""))
 
 _p = c_void_p  # device / host pointers are passed as raw addresses
 

@@ -8,7 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libsasvqa_b200.so")
+# development A/B builds: SASVQA_LIB_SUFFIX=_x SASVQA_DEFINES="-DFOO=1" -> libsasvqa_b200_x.so
+SUFFIX = os.environ.get("SASVQA_LIB_SUFFIX", "")
+LIB = os.path.join(HERE, f"libsasvqa_b200{SUFFIX}.so")
 SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "attention.cu", "attention_tcgen05.cu", "elementwise.cu", "select.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -36,9 +38,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    defines = os.environ.get("SASVQA_DEFINES", "").split()
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(HERE, "build", src.replace(".cu", f"{SUFFIX}.o"))
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

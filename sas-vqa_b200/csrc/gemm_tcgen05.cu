@@ -15,7 +15,7 @@
 //                swizzle, 6-stage ring; all transaction bytes land on the LEADER CTA's mbarrier
 //   warp 1     : TMEM allocator (both CTAs); in the leader CTA one lane issues the MMAs and
 //                tcgen05.commit-multicasts "stage free" / "accumulator full" to both CTAs
-//   warps 2..5 : epilogue (both CTAs, 128 accumulator rows each): tcgen05.ld -> registers ->
+//   warps 2..9 : epilogue (both CTAs, 128 accumulator rows each; two warps per TMEM lane quarter): tcgen05.ld -> registers ->
 //                fused elementwise -> 128B-swizzled smem staging -> TMA store (bf16 outputs) or
 //                TMA reduce-add (fp32 residual stream, performed in L2: x is never read by the
 //                SM); accumulators are double buffered (2 x 256 TMEM columns) so the epilogue of
@@ -34,17 +34,26 @@ constexpr int BLOCK_N = 256;          // UMMA N
 constexpr int HALF_N = 128;           // weight rows staged per CTA
 constexpr int BLOCK_K = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 6;
+#ifndef SASVQA_GEMM_STAGES
+#define SASVQA_GEMM_STAGES 6
+#endif
+#ifndef SASVQA_GEMM_EPI_WARPS
+#define SASVQA_GEMM_EPI_WARPS 8
+#endif
+constexpr int STAGES = SASVQA_GEMM_STAGES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;          // 512
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;     // 16 KiB
 constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;      // 16 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 192;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = SASVQA_GEMM_EPI_WARPS;   // 8: two warps per TMEM lane quarter, 128 accumulator columns each
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int EPI_BUF_BYTES = 32 * 128;                  // 32 rows x 128 B, one TMA store box
-constexpr int EPI_BUFS_PER_WARP = 2;
-constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS_PER_WARP * EPI_BUF_BYTES;   // 32 KiB
+#ifndef SASVQA_GEMM_EPI_BUFS
+#define SASVQA_GEMM_EPI_BUFS 1
+#endif
+constexpr int EPI_BUFS_PER_WARP = SASVQA_GEMM_EPI_BUFS;
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS_PER_WARP * EPI_BUF_BYTES;   // 64 KiB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
 
@@ -237,7 +246,7 @@ __device__ __forceinline__ void epilogue_bf16_chunk(const EpiParams& p, const CU
         packed[2 * q + 1] = pack_bf16x2(f2, f3);
     }
     // the TMA store issued two chunks ago read this buffer; make sure it is done with it
-    if (lane == 0) bulk_wait_read<1>();
+    if (lane == 0) bulk_wait_read<EPI_BUFS_PER_WARP - 1>();
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -257,7 +266,7 @@ __device__ __forceinline__ void epilogue_resid_chunk(const EpiParams& p, const C
     tcgen05_ld32(taddr, v);
     tcgen05_wait_ld();
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-    if (lane == 0) bulk_wait_read<1>();
+    if (lane == 0) bulk_wait_read<EPI_BUFS_PER_WARP - 1>();
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -398,6 +407,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else {
         // ===================== epilogue warps (both CTAs) =====================
         const int lane_grp = warp & 3;                      // TMEM lane quarter this warp may access
+        constexpr int COLS_PER_WARP = BLOCK_N / (NUM_EPI_WARPS / 4);
+        const int col_lo = ((warp - 2) >> 2) * COLS_PER_WARP;   // 8 warps: warps 2-5 columns [0,128), warps 6-9 [128,256)
+        const int col_hi = col_lo + COLS_PER_WARP;
         const uint32_t buf0 = epi_base + (uint32_t)((warp - 2) * EPI_BUFS_PER_WARP * EPI_BUF_BYTES);
         uint32_t t = 0, chunk_ctr = 0;
         for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++t) {
@@ -410,17 +422,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N);
             if (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 64, ++chunk_ctr)
+                for (int c = col_lo; c < col_hi; c += 64, ++chunk_ctr)
                     epilogue_bf16_chunk<MODE>(epi, &map_out, taddr + (uint32_t)c,
-                                              buf0 + (chunk_ctr & 1u) * EPI_BUF_BYTES, row0, n_blk * BLOCK_N + c, lane);
+                                              buf0 + (chunk_ctr % EPI_BUFS_PER_WARP) * EPI_BUF_BYTES, row0, n_blk * BLOCK_N + c, lane);
             } else if (MODE == EPI_BIAS_RESID_F32) {
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32, ++chunk_ctr)
-                    epilogue_resid_chunk(epi, &map_out, taddr + (uint32_t)c, buf0 + (chunk_ctr & 1u) * EPI_BUF_BYTES,
+                for (int c = col_lo; c < col_hi; c += 32, ++chunk_ctr)
+                    epilogue_resid_chunk(epi, &map_out, taddr + (uint32_t)c, buf0 + (chunk_ctr % EPI_BUFS_PER_WARP) * EPI_BUF_BYTES,
                                          row0, n_blk * BLOCK_N + c, lane);
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32)
+                for (int c = col_lo; c < col_hi; c += 32)
                     epilogue_patch_chunk(epi, taddr + (uint32_t)c, row0 + lane, n_blk * BLOCK_N + c);
             }
             tcgen05_fence_before();
