@@ -34,6 +34,10 @@ METRIC = "sampled videos/sec"
 UNIT = "videos/s"
 GEMM_FLOP_PER_FRAME = 2 * 196 * 768 * 768 + 12 * (2 * 197 * 768 * (2304 + 768 + 3072 + 3072))   # 33.70 GFLOP
 TOTAL_FLOP_PER_FRAME = GEMM_FLOP_PER_FRAME + 12 * (2 * 2 * 197 * 197 * 768)                       # 35.13 GFLOP
+# dram__bytes_read.sum + dram__bytes_write.sum of gemm_tcgen05_kernel from one `ncu --set full` capture at
+# chunk_frames=2048 (profiles/r01/ncu_gemm_v2_full.txt): qkv 2.43 GB, out_proj 3.04 GB, fc1 3.05 GB, fc2 5.16 GB
+# per launch -> mean over the four per-layer launches (the two patch-embed launches per step are negligible).
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = {2048: (2.428e9 + 3.041e9 + 3.047e9 + 5.158e9) / 4}
 
 
 def parse():
@@ -260,7 +264,10 @@ def run_ours(args):
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tf_sustained"],
-        "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sustained"],
+        "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH.get(args.chunk_frames),
+        "traffic_note": "mean DRAM bytes per GEMM launch from ncu (profiles/r01/ncu_gemm_v2_full.txt); algorithmic "
+                        "operand+result bytes average 3.4e9 per launch at this chunk size",
         "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
         "flop_per_launch": GEMM_FLOP_PER_FRAME * frames_timed / max(gemm_launches, 1),
         "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches": gemm_launches,
