@@ -181,7 +181,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_gpus):
@@ -338,14 +338,23 @@ def run_ours(args):
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     enc.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line: dict) -> None:
+    """The driver reads ONE JSON line from stdout: everything else (NCCL banners, library printf) was
+    re-routed to stderr at start-up, the line goes to the saved real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                 # C-level and Python-level stdout -> stderr from here on
     if a.impl == "reference":
         run_reference(a)
     else:

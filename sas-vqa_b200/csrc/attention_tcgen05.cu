@@ -9,10 +9,14 @@
 //   warp 1      MMA issuer: S_h = Q_h K^T  (M=128, N=208, K=64 -> 4 UMMAs, both operands K-major smem)
 //                           O_h = P_h V    (M=128, N=64, K=208 -> 13 UMMAs; A = P from TMEM, B = V as an
 //                                           MN-major smem operand, i.e. V exactly as TMA delivered it)
-//   warps 2-5   softmax + epilogue of query half h = 0 (rows 0..127), one thread per query row
-//   warps 6-9   same for half h = 1 (rows 128..196; rows >= 197 are skipped)
-// TMEM per half (256-column stride): S_h fp32 in columns [0,208); P_h = exp2(S - max) as packed bf16
-// overwrites columns [0,104) in place; O_h fp32 accumulates in columns [128,192).
+//   warps 2-9   softmax + epilogue.  All eight warps work on the same query half; the two warps that share
+//               a TMEM lane quarter (w, w+4) split a row's keys: part 0 = keys [0,112), part 1 = [112,208),
+//               exchanging the row max / row sum through shared memory.  Order per item:
+//               softmax(h=0), softmax(h=1), epilogue(h=0), epilogue(h=1) -- so P_0*V runs under softmax(h=1)
+//               and the next item's S MMAs run under the epilogues (two TMEM slots, ping-pong).
+// TMEM slot per half (256-column stride): S_h fp32 in columns [0,208); P = exp2(S - max) as packed bf16 is
+// written in place by each part over its own consumed columns: keys [0,112) -> columns [0,56), keys
+// [112,208) -> columns [112,160); O_h fp32 accumulates in columns [160,224).
 #include "common.cuh"
 
 namespace sasvqa {
@@ -25,7 +29,9 @@ constexpr int Q_BYTES = 2 * Q_HALF_BYTES;
 constexpr int KV_BYTES = KEYS * 128;              // 26 624
 constexpr int ITEM_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86 016 (multiple of 1024)
 constexpr int ATT_THREADS = 320;
-constexpr int ATT_SMEM = 2 * ITEM_BYTES + 1024 + 256;
+constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;       // row max + row sum exchange: [kind][half][part][128 rows] fp32
+constexpr int ATT_SMEM = 2 * ITEM_BYTES + XCH_BYTES + 1024 + 256;
+constexpr int O_COL = 160;                         // O accumulator columns inside a slot
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,7 +157,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                          __nv_bfloat16* __restrict__ out, int n_items, int variant) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + 2 * ITEM_BYTES;
+    const uint32_t xch_base = smem_base + 2 * ITEM_BYTES;
+    const uint32_t bar_base = xch_base + XCH_BYTES;
     auto kv_full = [&](int b) { return bar_base + 8u * b; };
     auto kv_empty = [&](int b) { return bar_base + 8u * (2 + b); };
     auto s_full = [&](int h) { return bar_base + 8u * (4 + h); };
@@ -167,9 +174,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             mbar_init(kv_full(b), 1);
             mbar_init(kv_empty(b), 1);
             mbar_init(s_full(b), 1);
-            mbar_init(p_full(b), 128);
+            mbar_init(p_full(b), 256);
             mbar_init(o_full(b), 1);
-            mbar_init(o_empty(b), 128);
+            mbar_init(o_empty(b), 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -204,157 +211,159 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // Issue order per item i:  S_0(i), PV_1(i-1), S_1(i), PV_0(i).  Half 1 trails half 0 by half an
-        // item, so the two softmax groups alternate on the (exp2-bound) SFU instead of running -- and then
-        // waiting on the tensor pipe -- in lockstep.
         if (lane == 0) {
-            auto issue_s = [&](uint32_t q_smem, uint32_t k_smem, int h) {
-                const uint64_t adesc = desc_sw128(q_smem + h * Q_HALF_BYTES, 0);
-                const uint64_t bdesc = desc_sw128(k_smem, 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_ss(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescS,
-                           k != 0);
-                tcgen05_commit(s_full(h));
-            };
-            auto issue_pv = [&](uint32_t v_smem, int h) {
-                const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
-#pragma unroll 1
-                for (int k = 0; k < KEYS / 16; ++k)              // 16 keys = 8 packed-bf16 TMEM columns = 2048 B of V
-                    mma_ts(tmem_base + (uint32_t)(h * 256 + 128), tmem_base + (uint32_t)(h * 256 + 8 * k),
-                           vdesc + (uint64_t)(128 * k), kIdescPV, k != 0);
-                tcgen05_commit(o_full(h));
-            };
             uint32_t it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int b = it & 1;
                 const uint32_t par = it & 1u;
                 const uint32_t q_smem = smem_base + b * ITEM_BYTES;
                 const uint32_t k_smem = q_smem + Q_BYTES, v_smem = k_smem + KV_BYTES;
-                const uint32_t v_prev = smem_base + (b ^ 1) * ITEM_BYTES + Q_BYTES + KV_BYTES;
                 mbar_wait(kv_full(b), (it >> 1) & 1u);
                 tcgen05_fence_after();
-                mbar_wait(o_empty(0), par ^ 1u);                // previous item's O_0 (and P_0) fully consumed
-                tcgen05_fence_after();
-                issue_s(q_smem, k_smem, 0);
-                if (it > 0) {
-                    mbar_wait(p_full(1), par ^ 1u);             // softmax wrote P_1 of the previous item
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(o_empty(h), par ^ 1u);            // previous item's O_h (and P_h) fully consumed
                     tcgen05_fence_after();
-                    issue_pv(v_prev, 1);
-                    tcgen05_commit(kv_empty(b ^ 1));            // previous item's Q/K/V smem reusable
+                    const uint64_t adesc = desc_sw128(q_smem + h * Q_HALF_BYTES, 0);
+                    const uint64_t bdesc = desc_sw128(k_smem, 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        mma_ss(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                               kIdescS, k != 0);
+                    tcgen05_commit(s_full(h));
                 }
-                mbar_wait(o_empty(1), par ^ 1u);
-                tcgen05_fence_after();
-                issue_s(q_smem, k_smem, 1);
-                mbar_wait(p_full(0), par);                      // softmax wrote P_0 of this item
-                tcgen05_fence_after();
-                issue_pv(v_smem, 0);
-            }
-            if (it > 0) {                                       // drain: half 1 of the last item
-                const uint32_t last = it - 1;
-                mbar_wait(p_full(1), last & 1u);
-                tcgen05_fence_after();
-                issue_pv(smem_base + (last & 1) * ITEM_BYTES + Q_BYTES + KV_BYTES, 1);
-                tcgen05_commit(kv_empty(last & 1));
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(p_full(h), par);                  // softmax wrote P_h into TMEM
+                    tcgen05_fence_after();
+                    const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
+#pragma unroll 1
+                    for (int k = 0; k < KEYS / 16; ++k) {        // 16 keys = 8 packed-bf16 TMEM columns = 2048 B of V
+                        const int pcol = k < 7 ? 8 * k : 112 + 8 * (k - 7);
+                        mma_ts(tmem_base + (uint32_t)(h * 256 + O_COL), tmem_base + (uint32_t)(h * 256 + pcol),
+                               vdesc + (uint64_t)(128 * k), kIdescPV, k != 0);
+                    }
+                    tcgen05_commit(o_full(h));
+                }
+                tcgen05_commit(kv_empty(b));                    // Q/K/V smem of this item reusable
             }
         }
     } else {
-        // ===================== softmax + epilogue: one thread per query row =====================
-        const int h = (warp - 2) >> 2;                          // query half
+        // ===================== softmax + epilogue =====================
         const int quarter = warp & 3;                           // TMEM lane quarter this warp may touch
-        const int qrow = h * 128 + quarter * 32 + lane;         // token index of this thread's query
-        const bool warp_active = (h * 128 + quarter * 32) < kTokens;
-        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
+        const int part = (warp - 2) >> 2;                       // 0: keys [0,112)   1: keys [112,208)
+        const int lrow = quarter * 32 + lane;                   // row inside the query half
+        const uint32_t pair_bar = 1u + (uint32_t)quarter;       // named barrier shared by warps (w, w+4)
+        float* xch = reinterpret_cast<float*>(smem_raw + (xch_base - smem_u32(smem_raw)));
+        auto xmax = [&](int h, int pt) -> float& { return xch[(h * 2 + pt) * 128 + lrow]; };
+        auto xsum = [&](int h, int pt) -> float& { return xch[512 + (h * 2 + pt) * 128 + lrow]; };
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t par = it & 1u;
             const int frame = item / kHeads, head = item - frame * kHeads;
-            mbar_wait(s_full(h), par);
-            tcgen05_fence_after();
-            float inv_l = 0.f;
-            if (warp_active) {
-                // ---- pass 1: row maximum over the 197 valid keys
-                float mx = -INFINITY;
-                if (variant & 1) mx = 30.0f;                    // timing experiment: no max pass
+            // ---------------- softmax of both halves
+            for (int h = 0; h < 2; ++h) {
+                const bool active = (h * 128 + quarter * 32) < kTokens;     // warp-uniform, same for both parts
+                const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
+                mbar_wait(s_full(h), par);
+                tcgen05_fence_after();
+                if (active) {
+                    const uint32_t s_col = part == 0 ? 0u : 112u;          // first S column of this part
+                    const uint32_t p_col = s_col;                            // P goes in place over the consumed S
+                    // ---- pass 1: max over this part's valid keys
+                    float mx = -INFINITY;
+                    if (variant & 1) mx = 30.0f;                // timing experiment: no max pass
 #pragma unroll 1
-                for (int c = 0; c < ((variant & 1) ? 0 : 6); ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(trow + (uint32_t)(32 * c), v);
-                    tmem_wait_ld();
+                    for (int c = 0; c < ((variant & 1) ? 0 : 3); ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(trow + s_col + (uint32_t)(32 * c), v);
+                        tmem_wait_ld();
+                        const int lim = kTokens - (int)s_col - 32 * c;       // valid columns in this chunk
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                }
-                {
-                    uint32_t v[16];
-                    tmem_ld16(trow + 192u, v);
-                    tmem_wait_ld();
+                        for (int j = 0; j < 32; ++j)
+                            if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                    if (part == 0 && !(variant & 1)) {
+                        uint32_t v[16];
+                        tmem_ld16(trow + 96u, v);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < kTokens - 192; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                }
-                const float m2 = mx * kScaleLog2e;
-                // ---- pass 2: P = exp2(S * scale - m2) -> packed bf16, in place over S; l = row sum
-                float l = 0.f;
+                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                    xmax(h, part) = mx;
+                    pair_sync();
+                    const float m2 = fmaxf(mx, xmax(h, part ^ 1)) * kScaleLog2e;
+                    // ---- pass 2: P = exp2(S * scale - m2) -> packed bf16 in place; partial row sum
+                    float l = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < 6; ++c) {
-                    uint32_t v[32], pk[16];
-                    tmem_ld32(trow + (uint32_t)(32 * c), v);
-                    tmem_wait_ld();
+                    for (int c = 0; c < 3; ++c) {
+                        uint32_t v[32], pk[16];
+                        tmem_ld32(trow + s_col + (uint32_t)(32 * c), v);
+                        tmem_wait_ld();
+                        const int lim = kTokens - (int)s_col - 32 * c;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float p0 = fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2);
-                        float p1 = fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2);
-                        if (!(variant & 2)) {                   // (variant & 2: timing experiment without the SFU)
-                            p0 = ex2(p0);
-                            p1 = ex2(p1);
+                        for (int j = 0; j < 16; ++j) {
+                            float p0 = fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2);
+                            float p1 = fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2);
+                            if (!(variant & 2)) {               // (variant & 2: timing experiment without the SFU)
+                                p0 = ex2(p0);
+                                p1 = ex2(p1);
+                            }
+                            p0 = (2 * j < lim) ? p0 : 0.f;      // keys >= 197 contribute nothing
+                            p1 = (2 * j + 1 < lim) ? p1 : 0.f;
+                            l += p0 + p1;
+                            pk[j] = pack_bf16x2(p0, p1);
                         }
-                        l += p0 + p1;
-                        pk[j] = pack_bf16x2(p0, p1);
+                        tmem_st16(trow + p_col + (uint32_t)(16 * c), pk);
                     }
-                    tmem_st16(trow + (uint32_t)(16 * c), pk);
+                    if (part == 0) {
+                        uint32_t v[16], pk[8];
+                        tmem_ld16(trow + 96u, v);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2));
+                            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2));
+                            l += p0 + p1;
+                            pk[j] = pack_bf16x2(p0, p1);
+                        }
+                        tmem_st8(trow + 48u, pk);
+                    }
+                    tmem_wait_st();
+                    xsum(h, part) = l;
                 }
-                {
-                    uint32_t v[16], pk[8];
-                    tmem_ld16(trow + 192u, v);
+                tcgen05_fence_before();
+                mbar_arrive(p_full(h));
+            }
+            // ---------------- epilogues: O_h / l -> bf16 -> out[token, head*64 + part*32 .. +32)
+            for (int h = 0; h < 2; ++h) {
+                const bool active = (h * 128 + quarter * 32) < kTokens;
+                const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
+                const int qrow = h * 128 + lrow;
+                mbar_wait(o_full(h), par);
+                tcgen05_fence_after();
+                if (active) {
+                    uint32_t o[32];
+                    tmem_ld32(trow + (uint32_t)(O_COL + 32 * part), o);
+                    pair_sync();                                // partner's partial row sum is in smem
+                    const float inv_l = 1.0f / (xsum(h, 0) + xsum(h, 1));
                     tmem_wait_ld();
+                    if (qrow < kTokens) {
+                        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + qrow) * kHidden +
+                                                              head * kHeadDim + part * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float p0 = (2 * j < kTokens - 192) ? ex2(fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2)) : 0.f;
-                        const float p1 = (2 * j + 1 < kTokens - 192) ? ex2(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2)) : 0.f;
-                        l += p0 + p1;
-                        pk[j] = pack_bf16x2(p0, p1);
-                    }
-                    tmem_st8(trow + 96u, pk);
-                }
-                tmem_wait_st();
-                inv_l = 1.0f / l;
-            }
-            tcgen05_fence_before();
-            mbar_arrive(p_full(h));
-            // ---- epilogue: O_h / l -> bf16 -> out[token, head*64 .. +64)
-            mbar_wait(o_full(h), par);
-            tcgen05_fence_after();
-            if (warp_active) {
-                uint32_t o0[32], o1[32];
-                tmem_ld32(trow + 128u, o0);
-                tmem_ld32(trow + 160u, o1);
-                tmem_wait_ld();
-                if (qrow < kTokens) {
-                    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + qrow) * kHidden + head * kHeadDim);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t* o = q < 4 ? o0 : o1;
-                        const int e = (q & 3) * 8;
-                        uint4 w;
-                        w.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv_l, __uint_as_float(o[e + 1]) * inv_l);
-                        w.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv_l, __uint_as_float(o[e + 3]) * inv_l);
-                        w.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv_l, __uint_as_float(o[e + 5]) * inv_l);
-                        w.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv_l, __uint_as_float(o[e + 7]) * inv_l);
-                        dst[q] = w;
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 w;
+                            w.x = pack_bf16x2(__uint_as_float(o[8 * q + 0]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l);
+                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
+                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
+                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
+                            dst[q] = w;
+                        }
                     }
                 }
+                tcgen05_fence_before();
+                mbar_arrive(o_empty(h));
             }
-            tcgen05_fence_before();
-            mbar_arrive(o_empty(h));
         }
     }
 
