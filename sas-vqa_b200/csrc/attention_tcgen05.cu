@@ -8,15 +8,21 @@
 //   warp 0      TMA: Q (2 x 128 rows), K, V (208 rows) -> 128B-swizzled smem, double buffered
 //   warp 1      MMA issuer: S_h = Q_h K^T  (M=128, N=208, K=64 -> 4 UMMAs, both operands K-major smem)
 //                           O_h = P_h V    (M=128, N=64, K=208 -> 13 UMMAs; A = P from TMEM, B = V as an
-//                                           MN-major smem operand, i.e. V exactly as TMA delivered it)
+//                                           MN-major smem operand, i.e. V exactly as TMA delivered it).
+//               Back-to-back UMMAs into ONE accumulator are latency-chained (~150 cycles each at N=64,
+//               measured), so P V runs as two independent chains -- keys [0,112) -> O_a, keys [112,208) ->
+//               O_b, issued alternately -- and the epilogue adds the two accumulators.
 //   warps 2-9   softmax + epilogue.  All eight warps work on the same query half; the two warps that share
 //               a TMEM lane quarter (w, w+4) split a row's keys: part 0 = keys [0,112), part 1 = [112,208),
-//               exchanging the row max / row sum through shared memory.  Order per item:
+//               exchanging the row max / row sum through shared memory.  Each thread reads its scores from
+//               TMEM once and keeps them in registers.  Order per item:
 //               softmax(h=0), softmax(h=1), epilogue(h=0), epilogue(h=1) -- so P_0*V runs under softmax(h=1)
 //               and the next item's S MMAs run under the epilogues (two TMEM slots, ping-pong).
-// TMEM slot per half (256-column stride): S_h fp32 in columns [0,208); P = exp2(S - max) as packed bf16 is
-// written in place by each part over its own consumed columns: keys [0,112) -> columns [0,56), keys
-// [112,208) -> columns [112,160); O_h fp32 accumulates in columns [160,224).
+//               Epilogue: (O_a + O_b) / l -> bf16 -> 128B-swizzled smem slab of 32 rows -> one TMA store per
+//               warp pair (row stride in global memory is 1536 B: direct stores would be 64-byte fragments).
+// TMEM slot per half (256-column stride): S_h fp32 in columns [0,208); P = exp2(S - max) as packed bf16 goes
+// to columns [0,104) (part 0: [0,56), part 1: [56,104) -- written only after both parts hold their scores in
+// registers); O_a in [104,168), O_b in [168,232).
 #include "common.cuh"
 
 namespace sasvqa {
@@ -30,8 +36,11 @@ constexpr int KV_BYTES = KEYS * 128;              // 26 624
 constexpr int ITEM_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86 016 (multiple of 1024)
 constexpr int ATT_THREADS = 320;
 constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;       // row max + row sum exchange: [kind][half][part][128 rows] fp32
-constexpr int ATT_SMEM = 2 * ITEM_BYTES + XCH_BYTES + 1024 + 256;
-constexpr int O_COL = 160;                         // O accumulator columns inside a slot
+constexpr int SLAB_BYTES = 32 * 128;                 // output staging: 32 query rows x 64 bf16 of one head
+constexpr int STAGE_BYTES = 2 * 4 * SLAB_BYTES;      // [half][quarter]
+constexpr int ATT_SMEM = 2 * ITEM_BYTES + STAGE_BYTES + XCH_BYTES + 1024 + 256;
+constexpr int P1_COL = 56;                         // packed-bf16 P of part 1 (keys [112,208)) inside a slot
+constexpr int OA_COL = 104, OB_COL = 168;          // the two O accumulators inside a slot
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,7 +57,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifdef SASVQA_ATT_POLL
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -71,6 +84,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -95,7 +120,7 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -107,7 +132,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -116,7 +141,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -124,7 +149,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
@@ -135,6 +160,84 @@ __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) {      // FMNMX3
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {   // FFMA2
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {               // FADD2
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// One thread's share of a softmax row: the NV = 112 (part 0, S columns [0,112)) or 96 (part 1, S columns
+// [112,208), of which 85 are real keys) scores are read from TMEM ONCE into registers; the row max is combined
+// with the partner warp through shared memory; P = exp2(S*scale - max) goes back as packed bf16 over the
+// consumed columns.  Returns this part's partial row sum (fp32, before the bf16 rounding of P).
+template <int PART, class Exchange>
+__device__ __forceinline__ float softmax_part(uint32_t trow, Exchange&& exchange_max) {
+    constexpr int NV = PART == 0 ? 112 : 96;
+    constexpr int VALID = PART == 0 ? 112 : kTokens - 112;
+    constexpr uint32_t S_COL = PART == 0 ? 0u : 112u;
+    constexpr uint32_t P_COL = PART == 0 ? 0u : (uint32_t)P1_COL;
+    uint32_t v[NV];
+    tmem_ld32(trow + S_COL, v);
+    tmem_ld32(trow + S_COL + 32u, v + 32);
+    tmem_ld32(trow + S_COL + 64u, v + 64);
+    if (PART == 0) tmem_ld16(trow + 96u, v + 96);
+    tmem_wait_ld();
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < VALID; j += 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int a = j + 2 * c, b = a + 1;
+            if (b < VALID) mx[c] = max3(mx[c], __uint_as_float(v[a]), __uint_as_float(v[b]));
+            else if (a < VALID) mx[c] = fmaxf(mx[c], __uint_as_float(v[a]));
+        }
+    }
+    const float m2 = exchange_max(max3(mx[0], mx[1], fmaxf(mx[2], mx[3]))) * kScaleLog2e;
+    const uint64_t scale2 = pack_f32x2(kScaleLog2e, kScaleLog2e), neg_m2 = pack_f32x2(-m2, -m2);
+    uint64_t acc[2] = {0ull, 0ull};
+    uint32_t pk[NV / 2];
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) {
+        if (2 * j >= VALID) {                                   // keys >= 197 contribute nothing
+            pk[j] = 0u;
+            continue;
+        }
+        float p0, p1;
+        unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), scale2, neg_m2), p0, p1);
+        p0 = ex2(p0);
+        p1 = ex2(p1);
+        if (2 * j + 1 >= VALID) p1 = 0.f;
+        acc[j & 1] = add_f32x2(acc[j & 1], pack_f32x2(p0, p1));
+        pk[j] = pack_bf16x2(p0, p1);
+    }
+    tmem_st16(trow + P_COL, pk);
+    tmem_st16(trow + P_COL + 16u, pk + 16);
+    tmem_st16(trow + P_COL + 32u, pk + 32);
+    if (PART == 0) tmem_st8(trow + 48u, pk + 48);
+    float l0, l1;
+    unpack_f32x2(add_f32x2(acc[0], acc[1]), l0, l1);
+    tmem_wait_st();
+    return l0 + l1;
 }
 
 // smem operand descriptors, 128B swizzle, 1024 B between 8-row groups (see gemm_tcgen05.cu)
@@ -152,12 +255,26 @@ constexpr uint32_t kIdescS = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KE
 // O = P V   : M=128, N=64, A (TMEM) K-major, B MN-major (bit 16): V rows are keys with d contiguous
 constexpr uint32_t kIdescPV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
+// Development aid (build with -DSASVQA_ATT_TRACE): CTA 0 stamps clock64() at the protocol events of its first
+// items; launch_attention_tcgen05 prints the table.  Compiled out of the product library.
+#ifdef SASVQA_ATT_TRACE
+__device__ long long g_att_trace[16 * 3 * 16];
+#define TR(role, ev)                                                                                   \
+    do {                                                                                               \
+        if (blockIdx.x == 0 && lane == 0 && it < 16) g_att_trace[(it * 3 + (role)) * 16 + (ev)] = clock64(); \
+    } while (0)
+#else
+#define TR(role, ev) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                         __nv_bfloat16* __restrict__ out, int n_items, int variant) {
+                         const __grid_constant__ CUtensorMap map_out, __nv_bfloat16* __restrict__ out, int n_items,
+                         int variant) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t xch_base = smem_base + 2 * ITEM_BYTES;
+    const uint32_t stage_base = smem_base + 2 * ITEM_BYTES;
+    const uint32_t xch_base = stage_base + STAGE_BYTES;
     const uint32_t bar_base = xch_base + XCH_BYTES;
     auto kv_full = [&](int b) { return bar_base + 8u * b; };
     auto kv_empty = [&](int b) { return bar_base + 8u * (2 + b); };
@@ -178,9 +295,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             mbar_init(o_full(b), 1);
             mbar_init(o_empty(b), 256);
         }
+        mbar_init(bar_base + 8u * 14, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512)
@@ -220,9 +339,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 const uint32_t k_smem = q_smem + Q_BYTES, v_smem = k_smem + KV_BYTES;
                 mbar_wait(kv_full(b), (it >> 1) & 1u);
                 tcgen05_fence_after();
+                TR(0, 0);
                 for (int h = 0; h < 2; ++h) {
                     mbar_wait(o_empty(h), par ^ 1u);            // previous item's O_h (and P_h) fully consumed
                     tcgen05_fence_after();
+                    TR(0, 1 + h);
                     const uint64_t adesc = desc_sw128(q_smem + h * Q_HALF_BYTES, 0);
                     const uint64_t bdesc = desc_sw128(k_smem, 0);
 #pragma unroll
@@ -230,20 +351,35 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                         mma_ss(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
                                kIdescS, k != 0);
                     tcgen05_commit(s_full(h));
+#ifdef SASVQA_ATT_TRACE_MMA
+                    tcgen05_commit(bar_base + 8u * 14);
+                    mbar_wait(bar_base + 8u * 14, (it * 4 + h) & 1u);
+                    TR(0, 6 + h);
+#endif
                 }
                 for (int h = 0; h < 2; ++h) {
                     mbar_wait(p_full(h), par);                  // softmax wrote P_h into TMEM
                     tcgen05_fence_after();
+                    TR(0, 3 + h);
                     const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
-#pragma unroll 1
-                    for (int k = 0; k < KEYS / 16; ++k) {        // 16 keys = 8 packed-bf16 TMEM columns = 2048 B of V
-                        const int pcol = k < 7 ? 8 * k : 112 + 8 * (k - 7);
-                        mma_ts(tmem_base + (uint32_t)(h * 256 + O_COL), tmem_base + (uint32_t)(h * 256 + pcol),
-                               vdesc + (uint64_t)(128 * k), kIdescPV, k != 0);
+                    const uint32_t slot = tmem_base + (uint32_t)(h * 256);
+                    // 16 keys per UMMA = 8 packed-bf16 TMEM columns of P = 2048 B of V; chains a / b alternate
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) {
+                        mma_ts(slot + OA_COL, slot + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), kIdescPV, j != 0);
+                        if (j < 6)
+                            mma_ts(slot + OB_COL, slot + (uint32_t)(8 * (7 + j)), vdesc + (uint64_t)(128 * (7 + j)), kIdescPV,
+                                   j != 0);
                     }
                     tcgen05_commit(o_full(h));
+#ifdef SASVQA_ATT_TRACE_MMA
+                    tcgen05_commit(bar_base + 8u * 14);
+                    mbar_wait(bar_base + 8u * 14, (it * 4 + 2 + h) & 1u);
+                    TR(0, 8 + h);
+#endif
                 }
                 tcgen05_commit(kv_empty(b));                    // Q/K/V smem of this item reusable
+                TR(0, 5);
             }
         }
     } else {
@@ -256,6 +392,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         auto xmax = [&](int h, int pt) -> float& { return xch[(h * 2 + pt) * 128 + lrow]; };
         auto xsum = [&](int h, int pt) -> float& { return xch[512 + (h * 2 + pt) * 128 + lrow]; };
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+        const bool issuer = part == 0 && lane == 0;             // issues this warp pair's TMA stores
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t par = it & 1u;
@@ -266,105 +403,69 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
                 mbar_wait(s_full(h), par);
                 tcgen05_fence_after();
-                if (active) {
-                    const uint32_t s_col = part == 0 ? 0u : 112u;          // first S column of this part
-                    const uint32_t p_col = s_col;                            // P goes in place over the consumed S
-                    // ---- pass 1: max over this part's valid keys
-                    float mx = -INFINITY;
-                    if (variant & 1) mx = 30.0f;                // timing experiment: no max pass
-#pragma unroll 1
-                    for (int c = 0; c < ((variant & 1) ? 0 : 3); ++c) {
-                        uint32_t v[32];
-                        tmem_ld32(trow + s_col + (uint32_t)(32 * c), v);
-                        tmem_wait_ld();
-                        const int lim = kTokens - (int)s_col - 32 * c;       // valid columns in this chunk
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    }
-                    if (part == 0 && !(variant & 1)) {
-                        uint32_t v[16];
-                        tmem_ld16(trow + 96u, v);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    }
-                    xmax(h, part) = mx;
-                    pair_sync();
-                    const float m2 = fmaxf(mx, xmax(h, part ^ 1)) * kScaleLog2e;
-                    // ---- pass 2: P = exp2(S * scale - m2) -> packed bf16 in place; partial row sum
-                    float l = 0.f;
-#pragma unroll 1
-                    for (int c = 0; c < 3; ++c) {
-                        uint32_t v[32], pk[16];
-                        tmem_ld32(trow + s_col + (uint32_t)(32 * c), v);
-                        tmem_wait_ld();
-                        const int lim = kTokens - (int)s_col - 32 * c;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float p0 = fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2);
-                            float p1 = fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2);
-                            if (!(variant & 2)) {               // (variant & 2: timing experiment without the SFU)
-                                p0 = ex2(p0);
-                                p1 = ex2(p1);
-                            }
-                            p0 = (2 * j < lim) ? p0 : 0.f;      // keys >= 197 contribute nothing
-                            p1 = (2 * j + 1 < lim) ? p1 : 0.f;
-                            l += p0 + p1;
-                            pk[j] = pack_bf16x2(p0, p1);
-                        }
-                        tmem_st16(trow + p_col + (uint32_t)(16 * c), pk);
-                    }
-                    if (part == 0) {
-                        uint32_t v[16], pk[8];
-                        tmem_ld16(trow + 96u, v);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float p0 = ex2(fmaf(__uint_as_float(v[2 * j]), kScaleLog2e, -m2));
-                            const float p1 = ex2(fmaf(__uint_as_float(v[2 * j + 1]), kScaleLog2e, -m2));
-                            l += p0 + p1;
-                            pk[j] = pack_bf16x2(p0, p1);
-                        }
-                        tmem_st8(trow + 48u, pk);
-                    }
-                    tmem_wait_st();
+                if (quarter == 2) TR(1 + part, 0 + 4 * h);
+                if (active && !(variant & 8)) {                 // (variant & 8: timing experiment, protocol only)
+                    auto exchange_max = [&](float mx) {
+                        xmax(h, part) = mx;
+                        pair_sync();
+                        return fmaxf(mx, xmax(h, part ^ 1));
+                    };
+                    const float l = part == 0 ? softmax_part<0>(trow, exchange_max) : softmax_part<1>(trow, exchange_max);
                     xsum(h, part) = l;
                 }
+                if (quarter == 2) TR(1 + part, 1 + 4 * h);
                 tcgen05_fence_before();
                 mbar_arrive(p_full(h));
             }
-            // ---------------- epilogues: O_h / l -> bf16 -> out[token, head*64 + part*32 .. +32)
+            // ---------------- epilogues: (O_a + O_b) / l -> bf16 -> out[token, head*64 + part*32 .. +32)
             for (int h = 0; h < 2; ++h) {
-                const bool active = (h * 128 + quarter * 32) < kTokens;
+                const int row0 = h * 128 + quarter * 32;        // first query row of this warp pair
+                const bool active = row0 < kTokens;
+                const bool full_slab = row0 + 32 <= kTokens;    // all 32 rows are real tokens -> TMA store
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
-                const int qrow = h * 128 + lrow;
+                const uint32_t slab = stage_base + (uint32_t)((h * 4 + quarter) * SLAB_BYTES);
                 mbar_wait(o_full(h), par);
                 tcgen05_fence_after();
+                if (quarter == 2) TR(1 + part, 2 + 4 * h);
                 if (active) {
-                    uint32_t o[32];
-                    tmem_ld32(trow + (uint32_t)(O_COL + 32 * part), o);
-                    pair_sync();                                // partner's partial row sum is in smem
+                    uint32_t oa[32], ob[32];
+                    tmem_ld32(trow + (uint32_t)(OA_COL + 32 * part), oa);
+                    tmem_ld32(trow + (uint32_t)(OB_COL + 32 * part), ob);
+                    if (issuer) bulk_wait_read_all();           // the store that last read this slab is done with it
+                    pair_sync();                                // partner's partial row sum is in smem; slab is free
                     const float inv_l = 1.0f / (xsum(h, 0) + xsum(h, 1));
                     tmem_wait_ld();
-                    if (qrow < kTokens) {
-                        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + qrow) * kHidden +
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        w[j] = pack_bf16x2((__uint_as_float(oa[2 * j]) + __uint_as_float(ob[2 * j])) * inv_l,
+                                           (__uint_as_float(oa[2 * j + 1]) + __uint_as_float(ob[2 * j + 1])) * inv_l);
+                    if (full_slab) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)             // 16-byte chunk (part*4 + q) of row `lane`, 128B swizzle
+                            st_shared_v4(slab + (uint32_t)(lane * 128 + (((part * 4 + q) ^ (lane & 7)) << 4)), w[4 * q],
+                                         w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                        fence_proxy_async_smem();
+                    } else if (row0 + lane < kTokens && !(variant & 16)) {   // the 5 tail rows of a frame
+                        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + row0 + lane) * kHidden +
                                                               head * kHeadDim + part * 32);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 w;
-                            w.x = pack_bf16x2(__uint_as_float(o[8 * q + 0]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l);
-                            w.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l);
-                            w.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l);
-                            w.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l);
-                            dst[q] = w;
-                        }
+                        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
                     }
                 }
                 tcgen05_fence_before();
-                mbar_arrive(o_empty(h));
+                mbar_arrive(o_empty(h));                        // O_h is in registers: the slot may be overwritten
+                if (active && full_slab) {
+                    pair_sync();                                // both warps' chunks are in the slab
+                    if (issuer && !(variant & 16)) {
+                        tma_store_2d(&map_out, slab, head * kHeadDim, frame * kTokens + row0);
+                        bulk_commit();
+                    }
+                }
+                if (quarter == 2) TR(1 + part, 3 + 4 * h);
             }
         }
+        if (issuer) bulk_wait_all();
     }
 
     tcgen05_fence_before();
@@ -378,14 +479,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 }  // namespace
 
 // qkv viewed as bf16 [rows, 2304]; boxes of 64 columns (one head of q, k or v) x 128 rows (Q) / 208 rows (K, V)
-int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, const void* qkv, uint64_t rows) {
+// out viewed as bf16 [rows, 768]: boxes of 64 columns x 32 rows (one head of one warp pair's query rows)
+int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, CUtensorMap* map_out, const void* qkv, const void* out,
+                        uint64_t rows) {
     int rc = make_tensor_map_bf16_kmajor(map_q, qkv, rows, kQkv, 128);
     if (rc) return rc;
-    return make_tensor_map_bf16_kmajor(map_kv, qkv, rows, kQkv, KEYS);
+    if ((rc = make_tensor_map_bf16_kmajor(map_kv, qkv, rows, kQkv, KEYS))) return rc;
+    return make_tensor_map_out(map_out, out, rows, kHidden, 0);
 }
 
-int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int n_frames,
-                             int num_sms, cudaStream_t s, int variant) {
+int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, const CUtensorMap* map_out,
+                             __nv_bfloat16* out, int n_frames, int num_sms, cudaStream_t s, int variant) {
     if (n_frames == 0) return 0;
     SASVQA_REQUIRE(((uintptr_t)out & 15) == 0, "unaligned attention output");
     static bool attr_set = false;
@@ -396,9 +500,31 @@ int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv
     }
     const int n_items = n_frames * kHeads;
     const int grid = n_items < num_sms ? n_items : num_sms;
-    attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(*map_q, *map_kv, out, n_items, variant);
+    attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(*map_q, *map_kv, *map_out, out, n_items, variant);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
+#ifdef SASVQA_ATT_TRACE
+    {
+        static int shots = 0;
+        if (shots++ == 3) {
+            long long t[16 * 3 * 16];
+            cudaDeviceSynchronize();
+            cudaMemcpyFromSymbol(t, g_att_trace, sizeof(t));
+            const long long t0 = t[(2 * 3 + 0) * 16 + 0];
+            for (int it = 2; it < 8; ++it) {
+                printf("item %d  mma: kv %lld S0 %lld S1 %lld PV0 %lld PV1 %lld end %lld  [done: S0 %lld S1 %lld PV0 %lld PV1 %lld]\n", it, t[(it * 3) * 16 + 0] - t0,
+                       t[(it * 3) * 16 + 1] - t0, t[(it * 3) * 16 + 2] - t0, t[(it * 3) * 16 + 3] - t0,
+                       t[(it * 3) * 16 + 4] - t0, t[(it * 3) * 16 + 5] - t0, t[(it * 3) * 16 + 6] - t0, t[(it * 3) * 16 + 7] - t0,
+                       t[(it * 3) * 16 + 8] - t0, t[(it * 3) * 16 + 9] - t0);
+                for (int r = 1; r < 3; ++r)
+                    printf("        sm part %d: s0 %lld p0 %lld | s1 %lld p1 %lld | o0 %lld e0 %lld | o1 %lld e1 %lld\n", r - 1,
+                           t[(it * 3 + r) * 16 + 0] - t0, t[(it * 3 + r) * 16 + 1] - t0, t[(it * 3 + r) * 16 + 4] - t0,
+                           t[(it * 3 + r) * 16 + 5] - t0, t[(it * 3 + r) * 16 + 2] - t0, t[(it * 3 + r) * 16 + 3] - t0,
+                           t[(it * 3 + r) * 16 + 6] - t0, t[(it * 3 + r) * 16 + 7] - t0);
+            }
+        }
+    }
+#endif
     return 0;
 }
 

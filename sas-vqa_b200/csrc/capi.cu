@@ -126,13 +126,13 @@ int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, 
 }
 int sasvqa_test_attention(const uint16_t* qkv, int n_frames, uint16_t* out, int impl, void* stream) {
     if (impl == 1) return launch_attention(CBF(qkv), BF(out), n_frames, S(stream));
-    CUtensorMap mq, mkv;
-    int rc = make_attention_maps(&mq, &mkv, qkv, (uint64_t)n_frames * kTokens);
+    CUtensorMap mq, mkv, mo;
+    int rc = make_attention_maps(&mq, &mkv, &mo, qkv, out, (uint64_t)n_frames * kTokens);
     if (rc) return rc;
     int dev = 0, sms = 148;
     SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
     SASVQA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return launch_attention_tcgen05(&mq, &mkv, BF(out), n_frames, sms, S(stream), impl >= 10 ? impl - 10 : 0);
+    return launch_attention_tcgen05(&mq, &mkv, &mo, BF(out), n_frames, sms, S(stream), impl >= 10 ? impl - 10 : 0);
 }
 int sasvqa_test_layernorm(const float* x, int rows, const float* gamma, const float* beta, uint16_t* out, void* stream) {
     return launch_layernorm_bf16(x, BF(out), rows, gamma, beta, S(stream));

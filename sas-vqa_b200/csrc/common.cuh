@@ -84,9 +84,10 @@ int launch_layernorm_bf16(const float* x, __nv_bfloat16* h, int rows, const floa
 int launch_pool_norm(const float* x, int n_frames, const float* gamma, const float* beta, float* feats,
                      cudaStream_t s);
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, cudaStream_t s);   // mma.sync check kernel
-int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, const void* qkv, uint64_t rows);
-int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int n_frames,
-                             int num_sms, cudaStream_t s, int variant = 0);
+int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, CUtensorMap* map_out, const void* qkv, const void* out,
+                        uint64_t rows);
+int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, const CUtensorMap* map_out,
+                             __nv_bfloat16* out, int n_frames, int num_sms, cudaStream_t s, int variant = 0);
 int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s);
 int launch_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status,
                       cudaStream_t s);

@@ -70,7 +70,7 @@ struct SasvqaEncoder {
     __nv_bfloat16* h = nullptr;       // [chunk*197, 768]  LN output / attention output
     __nv_bfloat16* big = nullptr;     // [chunk*197, 3072] qkv (as [.,2304]) / fc1 output / patch matrix (as [chunk*196,768])
     CUtensorMap m_h, m_big_fc, m_big_patch;       // A-operand views
-    CUtensorMap m_att_q, m_att_kv;                // attention operand views of big as [., 2304]
+    CUtensorMap m_att_q, m_att_kv, m_att_out;     // attention operand views of big as [., 2304]; output view of h
     bool use_mma_attention = false;               // SASVQA_DEBUG_MMA_ATTENTION=1: legacy mma.sync kernel (bisecting aid)
     CUtensorMap m_out_qkv, m_out_fc1, m_out_x;    // TMA-store views of big ([.,2304] / [.,3072]) and x
     // scratch for the whole-path entry points (grown on demand)
@@ -161,7 +161,7 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
         {
             Scope sc(e, PK_ATTENTION, s);
             if (e->use_mma_attention) rc = launch_attention(e->big, e->h, n, s);
-            else rc = launch_attention_tcgen05(&e->m_att_q, &e->m_att_kv, e->h, n, e->num_sms, s);
+            else rc = launch_attention_tcgen05(&e->m_att_q, &e->m_att_kv, &e->m_att_out, e->h, n, e->num_sms, s);
             if (rc) return rc;
         }
         g = GemmArgs{};
@@ -304,7 +304,7 @@ int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames
     TRYCUDA(cudaMemset(e->h, 0, rows * kHidden * sizeof(__nv_bfloat16)));
     TRYCUDA(cudaMemset(e->big, 0, rows * kFfn * sizeof(__nv_bfloat16)));
     TRY(make_tensor_map_bf16_kmajor(&e->m_patch_w, e->w_patch, kHidden, kHidden, 128));
-    TRY(make_attention_maps(&e->m_att_q, &e->m_att_kv, e->big, rows));
+    TRY(make_attention_maps(&e->m_att_q, &e->m_att_kv, &e->m_att_out, e->big, e->h, rows));
     TRY(make_tensor_map_out(&e->m_out_qkv, e->big, rows, kQkv, 0));
     TRY(make_tensor_map_out(&e->m_out_fc1, e->big, rows, kFfn, 0));
     TRY(make_tensor_map_out(&e->m_out_x, e->x, rows, kHidden, 1));
