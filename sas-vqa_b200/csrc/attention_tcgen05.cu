@@ -4,22 +4,25 @@
 //
 // Input  qkv [n*197, 2304] bf16 (q | k | v).   Output out [n*197, 768] bf16 (heads concatenated).
 //
-// Persistent CTAs, one work item = (frame, head).  Per item:
-//   warp 0      TMA: Q (2 x 128 rows), K, V (208 rows) -> 128B-swizzled smem, double buffered
+// Persistent CTAs (512 threads, four warpgroups with setmaxnreg register budgets), one work item =
+// (frame, head), queries in two halves h of 128 rows.  Roles:
+//   warp 0      TMA: Q (2 x 128 rows) + K (208 rows) and V (208 rows) -> 128B-swizzled smem; the Q|K and the V
+//               buffers are double buffered and recycled separately (Q|K die after S, V after P V)
 //   warp 1      MMA issuer: S_h = Q_h K^T  (M=128, N=208, K=64 -> 4 UMMAs, both operands K-major smem)
 //                           O_h = P_h V    (M=128, N=64, K=208 -> 13 UMMAs; A = P from TMEM, B = V as an
 //                                           MN-major smem operand, i.e. V exactly as TMA delivered it).
 //               Back-to-back UMMAs into ONE accumulator are latency-chained (~150 cycles each at N=64,
 //               measured), so P V runs as two independent chains -- keys [0,112) -> O_a, keys [112,208) ->
 //               O_b, issued alternately -- and the epilogue adds the two accumulators.
-//   warps 2-9   softmax + epilogue.  All eight warps work on the same query half; the two warps that share
-//               a TMEM lane quarter (w, w+4) split a row's keys: part 0 = keys [0,112), part 1 = [112,208),
-//               exchanging the row max / row sum through shared memory.  Each thread reads its scores from
-//               TMEM once and keeps them in registers.  Order per item:
-//               softmax(h=0), softmax(h=1), epilogue(h=0), epilogue(h=1) -- so P_0*V runs under softmax(h=1)
-//               and the next item's S MMAs run under the epilogues (two TMEM slots, ping-pong).
-//               Epilogue: (O_a + O_b) / l -> bf16 -> 128B-swizzled smem slab of 32 rows -> one TMA store per
-//               warp pair (row stride in global memory is 1536 B: direct stores would be 64-byte fragments).
+//               Issue order: PV_0(i), S_0(i+1), PV_1(i), S_1(i+1): the next item's scores are ready before
+//               the softmax warps finish the current item.
+//   warps 4-11  softmax only.  All eight warps work on the same query half; the two warps that share a TMEM
+//               lane quarter (w, w+4) split a row's keys: part 0 = keys [0,112), part 1 = [112,208), exchanging
+//               the row max through shared memory.  Each thread reads its scores from TMEM once and keeps
+//               them in registers.  This stage is MUFU (ex2) bound; everything else hides under it.
+//   warps 12-15 epilogue: (O_a + O_b) / l -> bf16 -> 128B-swizzled smem slab of 32 rows -> one TMA store per
+//               warp (row stride in global memory is 1536 B: direct stores would be 64-byte fragments).
+//               The TMEM slot is released as soon as O is in registers.
 // TMEM slot per half (256-column stride): S_h fp32 in columns [0,208); P = exp2(S - max) as packed bf16 goes
 // to columns [0,104) (part 0: [0,56), part 1: [56,104) -- written only after both parts hold their scores in
 // registers); O_a in [104,168), O_b in [168,232).
@@ -33,12 +36,14 @@ constexpr int KEYS = 208;                         // 197 keys padded to a multip
 constexpr int Q_HALF_BYTES = 128 * 128;           // 128 rows x 64 bf16
 constexpr int Q_BYTES = 2 * Q_HALF_BYTES;
 constexpr int KV_BYTES = KEYS * 128;              // 26 624
-constexpr int ITEM_BYTES = Q_BYTES + 2 * KV_BYTES;   // 86 016 (multiple of 1024)
-constexpr int ATT_THREADS = 320;
-constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;       // row max + row sum exchange: [kind][half][part][128 rows] fp32
+constexpr int QK_BYTES = Q_BYTES + KV_BYTES;         // 59 392 (multiple of 1024)
+constexpr int ATT_THREADS = 512;
+constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 168, REGS_EPILOGUE = 112;   // 128 * (56 + 2 * 168 + 112) = 64 512
+constexpr int XMAX_BYTES = 2 * 2 * 128 * 4;          // row max exchange: [half][part][128 rows] fp32
+constexpr int XSUM_BYTES = 2 * 2 * 2 * 128 * 4;      // partial row sums: [item parity][half][part][128 rows] fp32
 constexpr int SLAB_BYTES = 32 * 128;                 // output staging: 32 query rows x 64 bf16 of one head
 constexpr int STAGE_BYTES = 2 * 4 * SLAB_BYTES;      // [half][quarter]
-constexpr int ATT_SMEM = 2 * ITEM_BYTES + STAGE_BYTES + XCH_BYTES + 1024 + 256;
+constexpr int ATT_SMEM = 2 * QK_BYTES + 2 * KV_BYTES + STAGE_BYTES + XMAX_BYTES + XSUM_BYTES + 1024 + 256;
 constexpr int P1_COL = 56;                         // packed-bf16 P of part 1 (keys [112,208)) inside a slot
 constexpr int OA_COL = 104, OB_COL = 168;          // the two O accumulators inside a slot
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
@@ -156,6 +161,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -256,7 +265,8 @@ constexpr uint32_t kIdescS = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KE
 constexpr uint32_t kIdescPV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 // Development aid (build with -DSASVQA_ATT_TRACE): CTA 0 stamps clock64() at the protocol events of its first
-// items; launch_attention_tcgen05 prints the table.  Compiled out of the product library.
+// items (role 0 = MMA issuer, 1 = softmax warp 6, 2 = epilogue warp 14); launch_attention_tcgen05 prints the
+// table.  Compiled out of the product library.
 #ifdef SASVQA_ATT_TRACE
 __device__ long long g_att_trace[16 * 3 * 16];
 #define TR(role, ev)                                                                                   \
@@ -273,29 +283,34 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                          int variant) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t stage_base = smem_base + 2 * ITEM_BYTES;
-    const uint32_t xch_base = stage_base + STAGE_BYTES;
-    const uint32_t bar_base = xch_base + XCH_BYTES;
-    auto kv_full = [&](int b) { return bar_base + 8u * b; };
-    auto kv_empty = [&](int b) { return bar_base + 8u * (2 + b); };
-    auto s_full = [&](int h) { return bar_base + 8u * (4 + h); };
-    auto p_full = [&](int h) { return bar_base + 8u * (6 + h); };
-    auto o_full = [&](int h) { return bar_base + 8u * (8 + h); };
-    auto o_empty = [&](int h) { return bar_base + 8u * (10 + h); };
-    const uint32_t tmem_slot = bar_base + 8u * 12;
+    const uint32_t v_base = smem_base + 2 * QK_BYTES;
+    const uint32_t stage_base = v_base + 2 * KV_BYTES;
+    const uint32_t xmax_base = stage_base + STAGE_BYTES;
+    const uint32_t xsum_base = xmax_base + XMAX_BYTES;
+    const uint32_t bar_base = xsum_base + XSUM_BYTES;
+    auto qk_full = [&](int b) { return bar_base + 8u * b; };
+    auto qk_empty = [&](int b) { return bar_base + 8u * (2 + b); };
+    auto v_full = [&](int b) { return bar_base + 8u * (4 + b); };
+    auto v_empty = [&](int b) { return bar_base + 8u * (6 + b); };
+    auto s_full = [&](int h) { return bar_base + 8u * (8 + h); };
+    auto p_full = [&](int h) { return bar_base + 8u * (10 + h); };
+    auto o_full = [&](int h) { return bar_base + 8u * (12 + h); };
+    auto o_empty = [&](int h) { return bar_base + 8u * (14 + h); };
+    const uint32_t tmem_slot = bar_base + 8u * 16;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int b = 0; b < 2; ++b) {
-            mbar_init(kv_full(b), 1);
-            mbar_init(kv_empty(b), 1);
+            mbar_init(qk_full(b), 1);
+            mbar_init(qk_empty(b), 1);
+            mbar_init(v_full(b), 1);
+            mbar_init(v_empty(b), 1);
             mbar_init(s_full(b), 1);
             mbar_init(p_full(b), 256);
             mbar_init(o_full(b), 1);
-            mbar_init(o_empty(b), 256);
+            mbar_init(o_empty(b), 128);
         }
-        mbar_init(bar_base + 8u * 14, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
@@ -311,161 +326,186 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+    if (warp < 4) {
+        setmaxnreg_dec<REGS_CTRL>();
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
             uint32_t it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int b = it & 1;
+                const uint32_t free_par = ((it >> 1) & 1u) ^ 1u;
                 const int frame = item / kHeads, head = item - frame * kHeads;
-                mbar_wait(kv_empty(b), ((it >> 1) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(kv_full(b), ITEM_BYTES);
-                const uint32_t dst = smem_base + b * ITEM_BYTES;
                 const int row = frame * kTokens;
-                tma_load_2d(dst, &map_q, head * kHeadDim, row, kv_full(b));
-                tma_load_2d(dst + Q_HALF_BYTES, &map_q, head * kHeadDim, row + 128, kv_full(b));
-                tma_load_2d(dst + Q_BYTES, &map_kv, kHidden + head * kHeadDim, row, kv_full(b));
-                tma_load_2d(dst + Q_BYTES + KV_BYTES, &map_kv, 2 * kHidden + head * kHeadDim, row, kv_full(b));
+                const uint32_t qk = smem_base + b * QK_BYTES;
+                mbar_wait(qk_empty(b), free_par);
+                mbar_arrive_expect_tx(qk_full(b), QK_BYTES);
+                tma_load_2d(qk, &map_q, head * kHeadDim, row, qk_full(b));
+                tma_load_2d(qk + Q_HALF_BYTES, &map_q, head * kHeadDim, row + 128, qk_full(b));
+                tma_load_2d(qk + Q_BYTES, &map_kv, kHidden + head * kHeadDim, row, qk_full(b));
+                mbar_wait(v_empty(b), free_par);
+                mbar_arrive_expect_tx(v_full(b), KV_BYTES);
+                tma_load_2d(v_base + b * KV_BYTES, &map_kv, 2 * kHidden + head * kHeadDim, row, v_full(b));
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer =====================
+            auto issue_s = [&](uint32_t qk, int h) {           // S_h = Q_h K^T into slot h
+                const uint64_t adesc = desc_sw128(qk + h * Q_HALF_BYTES, 0);
+                const uint64_t bdesc = desc_sw128(qk + Q_BYTES, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mma_ss(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescS,
+                           k != 0);
+                tcgen05_commit(s_full(h));
+            };
+            auto issue_pv = [&](uint32_t v_smem, int h) {      // O_h = P_h V, two alternating accumulator chains
+                const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
+                const uint32_t slot = tmem_base + (uint32_t)(h * 256);
+                // 16 keys per UMMA = 8 packed-bf16 TMEM columns of P = 2048 B of V
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    mma_ts(slot + OA_COL, slot + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), kIdescPV, j != 0);
+                    if (j < 6)
+                        mma_ts(slot + OB_COL, slot + (uint32_t)(8 * (7 + j)), vdesc + (uint64_t)(128 * (7 + j)), kIdescPV,
+                               j != 0);
+                }
+                tcgen05_commit(o_full(h));
+            };
             uint32_t it = 0;
+            if ((int)blockIdx.x < n_items) {                    // prologue: scores of the first item
+                mbar_wait(qk_full(0), 0);
+                tcgen05_fence_after();
+                issue_s(smem_base, 0);
+                issue_s(smem_base, 1);
+                tcgen05_commit(qk_empty(0));
+            }
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int b = it & 1;
+                const int b = it & 1, nb = b ^ 1;
                 const uint32_t par = it & 1u;
-                const uint32_t q_smem = smem_base + b * ITEM_BYTES;
-                const uint32_t k_smem = q_smem + Q_BYTES, v_smem = k_smem + KV_BYTES;
-                mbar_wait(kv_full(b), (it >> 1) & 1u);
+                const bool has_next = item + (int)gridDim.x < n_items;
+                const uint32_t qk_next = smem_base + nb * QK_BYTES;
+                mbar_wait(v_full(b), (it >> 1) & 1u);
+                mbar_wait(p_full(0), par);                      // softmax wrote P_0 into TMEM
                 tcgen05_fence_after();
                 TR(0, 0);
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(o_empty(h), par ^ 1u);            // previous item's O_h (and P_h) fully consumed
+                issue_pv(v_base + b * KV_BYTES, 0);
+                if (has_next) {
+                    mbar_wait(qk_full(nb), ((it + 1) >> 1) & 1u);
+                    mbar_wait(o_empty(0), par);                 // epilogue holds O_0 in registers: slot 0 reusable
                     tcgen05_fence_after();
-                    TR(0, 1 + h);
-                    const uint64_t adesc = desc_sw128(q_smem + h * Q_HALF_BYTES, 0);
-                    const uint64_t bdesc = desc_sw128(k_smem, 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_ss(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                               kIdescS, k != 0);
-                    tcgen05_commit(s_full(h));
-#ifdef SASVQA_ATT_TRACE_MMA
-                    tcgen05_commit(bar_base + 8u * 14);
-                    mbar_wait(bar_base + 8u * 14, (it * 4 + h) & 1u);
-                    TR(0, 6 + h);
-#endif
+                    TR(0, 1);
+                    issue_s(qk_next, 0);
                 }
-                for (int h = 0; h < 2; ++h) {
-                    mbar_wait(p_full(h), par);                  // softmax wrote P_h into TMEM
+                mbar_wait(p_full(1), par);
+                tcgen05_fence_after();
+                TR(0, 2);
+                issue_pv(v_base + b * KV_BYTES, 1);
+                tcgen05_commit(v_empty(b));                     // V smem of this item reusable
+                if (has_next) {
+                    mbar_wait(o_empty(1), par);
                     tcgen05_fence_after();
-                    TR(0, 3 + h);
-                    const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
-                    const uint32_t slot = tmem_base + (uint32_t)(h * 256);
-                    // 16 keys per UMMA = 8 packed-bf16 TMEM columns of P = 2048 B of V; chains a / b alternate
-#pragma unroll
-                    for (int j = 0; j < 7; ++j) {
-                        mma_ts(slot + OA_COL, slot + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j), kIdescPV, j != 0);
-                        if (j < 6)
-                            mma_ts(slot + OB_COL, slot + (uint32_t)(8 * (7 + j)), vdesc + (uint64_t)(128 * (7 + j)), kIdescPV,
-                                   j != 0);
-                    }
-                    tcgen05_commit(o_full(h));
-#ifdef SASVQA_ATT_TRACE_MMA
-                    tcgen05_commit(bar_base + 8u * 14);
-                    mbar_wait(bar_base + 8u * 14, (it * 4 + 2 + h) & 1u);
-                    TR(0, 8 + h);
-#endif
+                    TR(0, 3);
+                    issue_s(qk_next, 1);
+                    tcgen05_commit(qk_empty(nb));               // Q|K smem of the next item reusable
                 }
-                tcgen05_commit(kv_empty(b));                    // Q/K/V smem of this item reusable
-                TR(0, 5);
             }
         }
-    } else {
-        // ===================== softmax + epilogue =====================
+    } else if (warp < 12) {
+        // ===================== softmax =====================
+        setmaxnreg_inc<REGS_SOFTMAX>();
         const int quarter = warp & 3;                           // TMEM lane quarter this warp may touch
-        const int part = (warp - 2) >> 2;                       // 0: keys [0,112)   1: keys [112,208)
+        const int part = (warp - 4) >> 2;                       // 0: keys [0,112)   1: keys [112,208)
         const int lrow = quarter * 32 + lane;                   // row inside the query half
         const uint32_t pair_bar = 1u + (uint32_t)quarter;       // named barrier shared by warps (w, w+4)
-        float* xch = reinterpret_cast<float*>(smem_raw + (xch_base - smem_u32(smem_raw)));
-        auto xmax = [&](int h, int pt) -> float& { return xch[(h * 2 + pt) * 128 + lrow]; };
-        auto xsum = [&](int h, int pt) -> float& { return xch[512 + (h * 2 + pt) * 128 + lrow]; };
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
-        const bool issuer = part == 0 && lane == 0;             // issues this warp pair's TMA stores
+        float* xmax = reinterpret_cast<float*>(smem_raw + (xmax_base - smem_u32(smem_raw)));
+        float* xsum = reinterpret_cast<float*>(smem_raw + (xsum_base - smem_u32(smem_raw)));
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t par = it & 1u;
-            const int frame = item / kHeads, head = item - frame * kHeads;
-            // ---------------- softmax of both halves
             for (int h = 0; h < 2; ++h) {
                 const bool active = (h * 128 + quarter * 32) < kTokens;     // warp-uniform, same for both parts
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
                 mbar_wait(s_full(h), par);
                 tcgen05_fence_after();
-                if (quarter == 2) TR(1 + part, 0 + 4 * h);
+                if (warp == 6) TR(1, 2 * h);
                 if (active && !(variant & 8)) {                 // (variant & 8: timing experiment, protocol only)
                     auto exchange_max = [&](float mx) {
-                        xmax(h, part) = mx;
-                        pair_sync();
-                        return fmaxf(mx, xmax(h, part ^ 1));
+                        xmax[(h * 2 + part) * 128 + lrow] = mx;
+                        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                        return fmaxf(mx, xmax[(h * 2 + (part ^ 1)) * 128 + lrow]);
                     };
                     const float l = part == 0 ? softmax_part<0>(trow, exchange_max) : softmax_part<1>(trow, exchange_max);
-                    xsum(h, part) = l;
+                    xsum[((par * 2 + h) * 2 + part) * 128 + lrow] = l;
                 }
-                if (quarter == 2) TR(1 + part, 1 + 4 * h);
+                if (warp == 6) TR(1, 2 * h + 1);
                 tcgen05_fence_before();
                 mbar_arrive(p_full(h));
             }
-            // ---------------- epilogues: (O_a + O_b) / l -> bf16 -> out[token, head*64 + part*32 .. +32)
+        }
+    } else {
+        // ===================== epilogue =====================
+        setmaxnreg_dec<REGS_EPILOGUE>();
+        const int quarter = warp & 3;
+        const int lrow = quarter * 32 + lane;
+        const float* xsum = reinterpret_cast<const float*>(smem_raw + (xsum_base - smem_u32(smem_raw)));
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const int frame = item / kHeads, head = item - frame * kHeads;
             for (int h = 0; h < 2; ++h) {
-                const int row0 = h * 128 + quarter * 32;        // first query row of this warp pair
+                const int row0 = h * 128 + quarter * 32;        // first query row of this warp
                 const bool active = row0 < kTokens;
                 const bool full_slab = row0 + 32 <= kTokens;    // all 32 rows are real tokens -> TMA store
                 const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 256);
                 const uint32_t slab = stage_base + (uint32_t)((h * 4 + quarter) * SLAB_BYTES);
+                mbar_wait(p_full(h), par);                      // the softmax warps' row sums are in smem
                 mbar_wait(o_full(h), par);
                 tcgen05_fence_after();
-                if (quarter == 2) TR(1 + part, 2 + 4 * h);
+                if (warp == 14) TR(2, 3 * h);
+                float o[64];
                 if (active) {
-                    uint32_t oa[32], ob[32];
-                    tmem_ld32(trow + (uint32_t)(OA_COL + 32 * part), oa);
-                    tmem_ld32(trow + (uint32_t)(OB_COL + 32 * part), ob);
-                    if (issuer) bulk_wait_read_all();           // the store that last read this slab is done with it
-                    pair_sync();                                // partner's partial row sum is in smem; slab is free
-                    const float inv_l = 1.0f / (xsum(h, 0) + xsum(h, 1));
-                    tmem_wait_ld();
-                    uint32_t w[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        w[j] = pack_bf16x2((__uint_as_float(oa[2 * j]) + __uint_as_float(ob[2 * j])) * inv_l,
-                                           (__uint_as_float(oa[2 * j + 1]) + __uint_as_float(ob[2 * j + 1])) * inv_l);
-                    if (full_slab) {
+                    for (int c = 0; c < 2; ++c) {               // two rounds of 32 columns keep the register peak low
+                        uint32_t oa[32], ob[32];
+                        tmem_ld32(trow + (uint32_t)(OA_COL + 32 * c), oa);
+                        tmem_ld32(trow + (uint32_t)(OB_COL + 32 * c), ob);
+                        tmem_wait_ld();
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)             // 16-byte chunk (part*4 + q) of row `lane`, 128B swizzle
-                            st_shared_v4(slab + (uint32_t)(lane * 128 + (((part * 4 + q) ^ (lane & 7)) << 4)), w[4 * q],
-                                         w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-                        fence_proxy_async_smem();
-                    } else if (row0 + lane < kTokens && !(variant & 16)) {   // the 5 tail rows of a frame
-                        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + row0 + lane) * kHidden +
-                                                              head * kHeadDim + part * 32);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                        for (int j = 0; j < 32; ++j) o[32 * c + j] = __uint_as_float(oa[j]) + __uint_as_float(ob[j]);
                     }
                 }
                 tcgen05_fence_before();
                 mbar_arrive(o_empty(h));                        // O_h is in registers: the slot may be overwritten
-                if (active && full_slab) {
-                    pair_sync();                                // both warps' chunks are in the slab
-                    if (issuer && !(variant & 16)) {
-                        tma_store_2d(&map_out, slab, head * kHeadDim, frame * kTokens + row0);
-                        bulk_commit();
+                if (warp == 14) TR(2, 3 * h + 1);
+                if (active) {
+                    const float* xs = xsum + (par * 2 + h) * 2 * 128 + lrow;
+                    const float inv_l = 1.0f / (xs[0] + xs[128]);
+                    uint32_t w[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w[j] = pack_bf16x2(o[2 * j] * inv_l, o[2 * j + 1] * inv_l);
+                    if (full_slab) {
+                        if (lane == 0) bulk_wait_read_all();    // the store that last read this slab is done with it
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)             // 16-byte chunk q of row `lane`, 128B swizzle
+                            st_shared_v4(slab + (uint32_t)(lane * 128 + ((q ^ (lane & 7)) << 4)), w[4 * q], w[4 * q + 1],
+                                         w[4 * q + 2], w[4 * q + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && !(variant & 16)) {
+                            tma_store_2d(&map_out, slab, head * kHeadDim, frame * kTokens + row0);
+                            bulk_commit();
+                        }
+                    } else if (row0 + lane < kTokens && !(variant & 16)) {   // the 5 tail rows of a frame
+                        uint4* dst =
+                            reinterpret_cast<uint4*>(out + ((size_t)frame * kTokens + row0 + lane) * kHidden + head * kHeadDim);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
                     }
                 }
-                if (quarter == 2) TR(1 + part, 3 + 4 * h);
+                if (warp == 14) TR(2, 3 * h + 2);
             }
         }
-        if (issuer) bulk_wait_all();
+        if (lane == 0) bulk_wait_all();
     }
 
     tcgen05_fence_before();
@@ -510,17 +550,13 @@ int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv
             long long t[16 * 3 * 16];
             cudaDeviceSynchronize();
             cudaMemcpyFromSymbol(t, g_att_trace, sizeof(t));
-            const long long t0 = t[(2 * 3 + 0) * 16 + 0];
+            const long long t0 = t[(2 * 3 + 1) * 16 + 0];
+            auto T = [&](int it, int role, int ev) { return t[(it * 3 + role) * 16 + ev] - t0; };
             for (int it = 2; it < 8; ++it) {
-                printf("item %d  mma: kv %lld S0 %lld S1 %lld PV0 %lld PV1 %lld end %lld  [done: S0 %lld S1 %lld PV0 %lld PV1 %lld]\n", it, t[(it * 3) * 16 + 0] - t0,
-                       t[(it * 3) * 16 + 1] - t0, t[(it * 3) * 16 + 2] - t0, t[(it * 3) * 16 + 3] - t0,
-                       t[(it * 3) * 16 + 4] - t0, t[(it * 3) * 16 + 5] - t0, t[(it * 3) * 16 + 6] - t0, t[(it * 3) * 16 + 7] - t0,
-                       t[(it * 3) * 16 + 8] - t0, t[(it * 3) * 16 + 9] - t0);
-                for (int r = 1; r < 3; ++r)
-                    printf("        sm part %d: s0 %lld p0 %lld | s1 %lld p1 %lld | o0 %lld e0 %lld | o1 %lld e1 %lld\n", r - 1,
-                           t[(it * 3 + r) * 16 + 0] - t0, t[(it * 3 + r) * 16 + 1] - t0, t[(it * 3 + r) * 16 + 4] - t0,
-                           t[(it * 3 + r) * 16 + 5] - t0, t[(it * 3 + r) * 16 + 2] - t0, t[(it * 3 + r) * 16 + 3] - t0,
-                           t[(it * 3 + r) * 16 + 6] - t0, t[(it * 3 + r) * 16 + 7] - t0);
+                printf("item %d  mma: PV0 %lld S0' %lld PV1 %lld S1' %lld\n", it, T(it, 0, 0), T(it, 0, 1), T(it, 0, 2), T(it, 0, 3));
+                printf("        softmax: s0 %lld p0 %lld | s1 %lld p1 %lld\n", T(it, 1, 0), T(it, 1, 1), T(it, 1, 2), T(it, 1, 3));
+                printf("        epilogue: o0 %lld free0 %lld end0 %lld | o1 %lld free1 %lld end1 %lld\n", T(it, 2, 0), T(it, 2, 1),
+                       T(it, 2, 2), T(it, 2, 3), T(it, 2, 4), T(it, 2, 5));
             }
         }
     }
