@@ -53,6 +53,12 @@ int sasvqa_encoder_create(const float* params_host, uint64_t n_params, int chunk
 void sasvqa_encoder_destroy(SasvqaEncoder* enc);
 int sasvqa_encoder_chunk_frames(const SasvqaEncoder* enc);
 
+/* ---- K0: resize + centre crop (frames that are not 224x224) -----------------------------------
+ * uint8 HWC [n, H, W, 3] -> uint8 HWC [n, 224, 224, 3]: shortest edge to 224 with the anti-aliased bicubic
+ * filter, then centre crop -- bit-exact with the host image processor's resize/crop
+ * (prefetch_loader.py:74-75 -> HF CLIPImageProcessor -> torchvision/ATen uint8 resampler). */
+int sasvqa_resize_crop_u8(const uint8_t* frames_hwc_dev, int n_frames, int H, int W, uint8_t* out_224_dev, void* stream);
+
 /* ---- K1: preprocessing ---------------------------------------------------------------------
  * uint8 HWC frames -> (x/255 - mean)/std -> bf16 patch matrix [n*196, 768], column = c*256+iy*16+ix.
  * Replaces the host image processor (prefetch_loader.py:74-75; 224x224 input) + the conv's im2col. */
@@ -97,6 +103,11 @@ int sasvqa_gather_frames_f32(const float* frames_dev, const int32_t* idx_dev, in
 int sasvqa_mdf_sample_u8(SasvqaEncoder* enc, const uint8_t* clips_hwc_dev, int B, int T, int K, int W,
                          int32_t* idx_dev, int32_t* status_dev, float* lcl_avg_or_null_dev,
                          float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
+/* same for decoded frames of any size [B, T, H, W, 3]: K0 runs per chunk in front of K1, and on the K picks
+ * of every clip in front of the gather (the sampled rows are the processor's output for those frames) */
+int sasvqa_mdf_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips_hwc_dev, int B, int T, int H, int W, int K,
+                            int Wwin, int32_t* idx_dev, int32_t* status_dev, float* lcl_avg_or_null_dev,
+                            float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
 /* same from normalised fp32 CHW frames [B, T, 3, 224, 224] (the reference sampler's input) */
 int sasvqa_mdf_sample_f32(SasvqaEncoder* enc, const float* clips_chw_dev, int B, int T, int K, int W,
                           int32_t* idx_dev, int32_t* status_dev, float* lcl_avg_or_null_dev,
@@ -109,13 +120,16 @@ int sasvqa_mdf_sample_f32(SasvqaEncoder* enc, const float* clips_chw_dev, int B,
 int sasvqa_mdf_sample_host(SasvqaEncoder* enc, const uint8_t* clips_hwc_host, int B, int T, int K, int W,
                            int32_t* idx_host, int32_t* status_host, float* sampled_or_null_host);
 
+int sasvqa_mdf_sample_host_hw(SasvqaEncoder* enc, const uint8_t* clips_hwc_host, int B, int T, int H, int W, int K,
+                              int Wwin, int32_t* idx_host, int32_t* status_host, float* sampled_or_null_host);
+
 /* ---- instrumentation ------------------------------------------------------------------------
  * sasvqa_launch_count: kernels launched by this library in this process so far.
  * Profiling: when enabled, CUDA-event pairs bracket every stage launch on its stream;
  * sasvqa_profile_read synchronises, sums milliseconds and scope counts per stage kind and resets.
  * Kinds: 0 preprocess, 1 gemm_patch_embed, 2 pre_layernorm, 3 layernorm, 4 gemm_qkv, 5 attention,
- * 6 gemm_out_proj, 7 gemm_fc1, 8 gemm_fc2, 9 pool_norm, 10 scores, 11 select, 12 gather. */
-#define SASVQA_PROFILE_KINDS 13
+ * 6 gemm_out_proj, 7 gemm_fc1, 8 gemm_fc2, 9 pool_norm, 10 scores, 11 select, 12 gather, 13 resize. */
+#define SASVQA_PROFILE_KINDS 14
 int64_t sasvqa_launch_count(void);
 int sasvqa_profile_enable(SasvqaEncoder* enc, int on);
 int sasvqa_profile_read(SasvqaEncoder* enc, double* ms_out, int64_t* scopes_out, int n_kinds);

@@ -182,10 +182,38 @@ def gen_encoder_and_e2e():
     np.savez_compressed(os.path.join(GOLD, "mdf_e2e_hf.npz"), **out)
 
 
+def gen_resize():
+    """The installed HF CLIPImageProcessor (the reference's `self.processor`, prefetch_loader.py:74) on frames
+    that need the shortest-edge bicubic resize + centre crop.  Its fp32 output is inverted to the uint8 image
+    it normalised (exactly recoverable: the map u -> (u - 255 mean) / (255 std) is injective on 0..255)."""
+    from transformers import CLIPImageProcessor
+    from oracle import resize
+    from oracle.resize import RESIZE_CASES, resize_case_frames
+    proc = CLIPImageProcessor()
+    mean = np.asarray(vit.IMAGE_MEAN, dtype=np.float64).reshape(1, 3, 1, 1)
+    std = np.asarray(vit.IMAGE_STD, dtype=np.float64).reshape(1, 3, 1, 1)
+    out = {"cases": np.asarray(RESIZE_CASES, dtype=np.int64)}
+    for h, w in RESIZE_CASES:
+        frames = resize_case_frames(h, w)
+        px = np.stack(proc(images=[f for f in frames])["pixel_values"])          # [2, 3, 224, 224] fp32
+        u = np.rint((px.astype(np.float64) * std + mean) * 255.0)
+        assert np.abs((u / 255.0 - mean) / std - px).max() < 1e-5
+        u8 = u.astype(np.uint8).transpose(0, 2, 3, 1)                              # [2, 224, 224, 3]
+        mine = resize.resize_crop_u8(frames)
+        print(f"resize {h}x{w}: restatement == HF processor: {np.array_equal(mine, u8)}")
+        out[f"out_{h}x{w}"] = u8
+        out[f"pixel_probe_{h}x{w}"] = px[:, :, ::37, ::41]
+    np.savez_compressed(os.path.join(GOLD, "resize_hf.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--resize-only" in sys.argv:
+        gen_resize()
+        sys.exit(0)
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     gen_mdf_select()
     gen_misc()
     gen_encoder_and_e2e()
+    gen_resize()

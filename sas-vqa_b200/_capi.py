@@ -20,6 +20,7 @@ SIGNATURES = {
     "sasvqa_encoder_create": (c_int, [_p, c_uint64, c_int, POINTER(c_void_p)]),
     "sasvqa_encoder_destroy": (None, [_p]),
     "sasvqa_encoder_chunk_frames": (c_int, [_p]),
+    "sasvqa_resize_crop_u8": (c_int, [_p, c_int, c_int, c_int, _p, _p]),
     "sasvqa_preprocess_u8": (c_int, [_p, c_int, _p, _p]),
     "sasvqa_patchify_f32": (c_int, [_p, c_int, _p, _p]),
     "sasvqa_encoder_fwd": (c_int, [_p, _p, c_int, _p, _p]),
@@ -31,7 +32,9 @@ SIGNATURES = {
     "sasvqa_gather_frames_f32": (c_int, [_p, _p, c_int, c_int, c_int, c_int64, _p, _p]),
     "sasvqa_mdf_sample_u8": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
     "sasvqa_mdf_sample_f32": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
+    "sasvqa_mdf_sample_u8_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
     "sasvqa_mdf_sample_host": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p]),
+    "sasvqa_mdf_sample_host_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_launch_count": (c_int64, []),
     "sasvqa_profile_enable": (c_int, [_p, c_int]),
     "sasvqa_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),

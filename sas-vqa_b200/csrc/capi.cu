@@ -18,9 +18,9 @@ void encoder_destroy(SasvqaEncoder*);
 int encoder_chunk_frames(const SasvqaEncoder*);
 int encoder_fwd(SasvqaEncoder*, const __nv_bfloat16*, int, float*, cudaStream_t);
 int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, cudaStream_t);
-int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int32_t*, int32_t*, float*,
-                      float*, float*, cudaStream_t);
-int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int32_t*, int32_t*, float*);
+int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int, int, int32_t*, int32_t*,
+                      float*, float*, float*, cudaStream_t);
+int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int, int, int32_t*, int32_t*, float*);
 
 }  // namespace sasvqa
 
@@ -92,16 +92,28 @@ int sasvqa_gather_frames_f32(const float* frames, const int32_t* idx, int B, int
 int sasvqa_mdf_sample_u8(SasvqaEncoder* enc, const uint8_t* clips, int B, int T, int K, int W, int32_t* idx,
                          int32_t* status, float* lcl_avg, float* feats, float* sampled, void* stream) {
     SASVQA_REQUIRE(B == 0 || T == 0 || clips != nullptr, "null clips");
-    return mdf_sample_device(enc, clips, nullptr, B, T, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+    return mdf_sample_device(enc, clips, nullptr, B, T, kImg, kImg, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+}
+int sasvqa_mdf_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips, int B, int T, int H, int Wd, int K, int W, int32_t* idx,
+                            int32_t* status, float* lcl_avg, float* feats, float* sampled, void* stream) {
+    SASVQA_REQUIRE(B == 0 || T == 0 || clips != nullptr, "null clips");
+    return mdf_sample_device(enc, clips, nullptr, B, T, H, Wd, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+}
+int sasvqa_resize_crop_u8(const uint8_t* frames, int n_frames, int H, int Wd, uint8_t* out, void* stream) {
+    return launch_resize_crop_u8(frames, n_frames, H, Wd, nullptr, 0, n_frames, out, S(stream));
 }
 int sasvqa_mdf_sample_f32(SasvqaEncoder* enc, const float* clips, int B, int T, int K, int W, int32_t* idx,
                           int32_t* status, float* lcl_avg, float* feats, float* sampled, void* stream) {
     SASVQA_REQUIRE(B == 0 || T == 0 || clips != nullptr, "null clips");
-    return mdf_sample_device(enc, nullptr, clips, B, T, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+    return mdf_sample_device(enc, nullptr, clips, B, T, kImg, kImg, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
 }
 int sasvqa_mdf_sample_host(SasvqaEncoder* enc, const uint8_t* clips_host, int B, int T, int K, int W, int32_t* idx_host,
                            int32_t* status_host, float* sampled_host) {
-    return mdf_sample_host(enc, clips_host, B, T, K, W, idx_host, status_host, sampled_host);
+    return mdf_sample_host(enc, clips_host, B, T, kImg, kImg, K, W, idx_host, status_host, sampled_host);
+}
+int sasvqa_mdf_sample_host_hw(SasvqaEncoder* enc, const uint8_t* clips_host, int B, int T, int H, int Wd, int K, int W,
+                              int32_t* idx_host, int32_t* status_host, float* sampled_host) {
+    return mdf_sample_host(enc, clips_host, B, T, H, Wd, K, W, idx_host, status_host, sampled_host);
 }
 
 int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, int mode, const float* bias_or_pos,

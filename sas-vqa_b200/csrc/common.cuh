@@ -75,6 +75,9 @@ int make_tensor_map_out(CUtensorMap* map, const void* base, uint64_t rows, uint6
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
+int launch_resize_crop_u8(const uint8_t* frames_hwc, long long n_src, int H, int W, const int32_t* frame_map,
+                          long long src_frame0, int n_out, uint8_t* out_224, cudaStream_t s);
+long long resize_source_bytes_per_frame(int H, int W);
 int launch_preprocess_u8(const uint8_t* frames_hwc, int n_frames, __nv_bfloat16* patches, cudaStream_t s);
 int launch_patchify_f32(const float* frames_chw, int n_frames, __nv_bfloat16* patches, cudaStream_t s);
 int launch_pre_layernorm(float* x, int n_frames, const float* cls_pos0, const float* gamma, const float* beta,

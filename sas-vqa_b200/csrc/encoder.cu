@@ -30,11 +30,20 @@ __global__ void fill_i32_kernel(int32_t* p, int32_t v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// selected (clip, index) pairs -> flat source frame numbers for the resize-on-gather path; picks < 0 stay < 0
+__global__ void frame_map_kernel(const int32_t* idx, int B, int T, int K, int32_t* map, int32_t* unit_idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K) return;
+    const int t = idx[i];
+    const bool ok = t >= 0 && t < T;
+    map[i] = ok ? (i / K) * T + t : -1;
+    unit_idx[i] = ok ? 0 : -1;
+}
 
 // profiling scopes (bench.py roofline): CUDA-event pairs around each stage's launches
 enum ProfKind {
     PK_PREPROCESS = 0, PK_GEMM_PATCH, PK_PRE_LN, PK_LN, PK_GEMM_QKV, PK_ATTENTION, PK_GEMM_OUT, PK_GEMM_FC1,
-    PK_GEMM_FC2, PK_POOL, PK_SCORES, PK_SELECT, PK_GATHER, PK_COUNT
+    PK_GEMM_FC2, PK_POOL, PK_SCORES, PK_SELECT, PK_GATHER, PK_RESIZE, PK_COUNT
 };
 struct ProfRec {
     int kind;
@@ -78,6 +87,13 @@ struct SasvqaEncoder {
     size_t feats_cap = 0;
     float* lcl = nullptr;
     size_t lcl_cap = 0;
+    // non-224 input: resized+cropped uint8 frames of one chunk / of the K picks, and the pick -> frame map
+    uint8_t* resized = nullptr;
+    size_t resized_cap = 0;
+    uint8_t* picked = nullptr;
+    size_t picked_cap = 0;
+    int32_t* pick_map = nullptr;
+    size_t pick_map_cap = 0;
     // host-buffer pipeline
     cudaStream_t h2d_stream = nullptr, compute_stream = nullptr, d2h_stream = nullptr;
     uint8_t* stage[2] = {nullptr, nullptr};
@@ -365,6 +381,7 @@ void encoder_destroy(SasvqaEncoder* e) {
     cudaFree(e->arena_bf16); cudaFree(e->arena_f32);
     cudaFree(e->x); cudaFree(e->h); cudaFree(e->big);
     cudaFree(e->feats); cudaFree(e->lcl);
+    cudaFree(e->resized); cudaFree(e->picked); cudaFree(e->pick_map);
     for (int i = 0; i < 2; ++i) {
         cudaFree(e->stage[i]); cudaFree(e->out_stage[i]); cudaFree(e->idx_stage[i]);
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
@@ -411,14 +428,21 @@ int encoder_fwd_hidden(SasvqaEncoder* e, const __nv_bfloat16* patches, int n_fra
 }
 
 // frames (uint8 HWC or fp32 CHW, device) -> feats [n_frames, 768], chunked through the workspace
-static int encode_frames(SasvqaEncoder* e, const uint8_t* u8, const float* f32, long long n_frames, float* feats,
-                         cudaStream_t s) {
+static int encode_frames(SasvqaEncoder* e, const uint8_t* u8, const float* f32, long long n_frames, int H, int W,
+                         float* feats, cudaStream_t s) {
+    const bool resize = u8 != nullptr && (H != kImg || W != kImg);
+    int rc;
+    if (resize && (rc = grow((void**)&e->resized, &e->resized_cap, (size_t)e->chunk_frames * kFrameElems))) return rc;
     for (long long f0 = 0; f0 < n_frames; f0 += e->chunk_frames) {
         const int n = (int)std::min<long long>(e->chunk_frames, n_frames - f0);
-        int rc;
+        if (resize) {                                            // K0: shortest-edge bicubic resize + centre crop
+            Scope sc(e, PK_RESIZE, s);
+            if ((rc = launch_resize_crop_u8(u8, n_frames, H, W, nullptr, f0, n, e->resized, s))) return rc;
+        }
         {
             Scope sc(e, PK_PREPROCESS, s);
-            if (u8) rc = launch_preprocess_u8(u8 + (size_t)f0 * kFrameElems, n, e->big, s);
+            if (resize) rc = launch_preprocess_u8(e->resized, n, e->big, s);
+            else if (u8) rc = launch_preprocess_u8(u8 + (size_t)f0 * kFrameElems, n, e->big, s);
             else rc = launch_patchify_f32(f32 + (size_t)f0 * kFrameElems, n, e->big, s);
             if (rc) return rc;
         }
@@ -431,10 +455,12 @@ static int encode_frames(SasvqaEncoder* e, const uint8_t* u8, const float* f32, 
     return 0;
 }
 
-int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int K, int W, int32_t* idx,
-                      int32_t* status, float* lcl_out, float* feats_out, float* sampled, cudaStream_t s) {
+int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int H, int Wd, int K, int W,
+                      int32_t* idx, int32_t* status, float* lcl_out, float* feats_out, float* sampled, cudaStream_t s) {
     SASVQA_REQUIRE(e != nullptr && idx != nullptr && status != nullptr, "null argument");
     SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 1, "bad B/T/K");
+    SASVQA_REQUIRE(H > 0 && Wd > 0, "bad frame size");
+    SASVQA_REQUIRE(u8 != nullptr || (H == kImg && Wd == kImg), "fp32 frames are already processed: they must be 224x224");
     SASVQA_REQUIRE(W >= -1, "W must be >= 0, or -1 for the adaptive width T / 20");
     if (B == 0) return 0;
     if (W == -1) W = T / 20;                                    // utils.py:32-33
@@ -457,7 +483,7 @@ int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
         if ((rc = grow((void**)&e->lcl, &e->lcl_cap, nf * sizeof(float)))) return rc;
         lcl = e->lcl;
     }
-    if ((rc = encode_frames(e, u8, f32, (long long)nf, feats, s))) return rc;
+    if ((rc = encode_frames(e, u8, f32, (long long)nf, H, Wd, feats, s))) return rc;
     {
         Scope sc(e, PK_SCORES, s);
         if ((rc = launch_mdf_scores(feats, B, T, W, lcl, nullptr, s))) return rc;
@@ -466,7 +492,21 @@ int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
         Scope sc(e, PK_SELECT, s);
         if ((rc = launch_mdf_select(lcl, B, T, K, W, idx, status, s))) return rc;
     }
-    if (sampled) {
+    if (sampled && u8 && (H != kImg || Wd != kImg)) {           // resize only the K picks of every clip, then gather
+        const size_t np = (size_t)B * K;
+        if ((rc = grow((void**)&e->picked, &e->picked_cap, np * kFrameElems))) return rc;
+        if ((rc = grow((void**)&e->pick_map, &e->pick_map_cap, 2 * np * sizeof(int32_t)))) return rc;
+        int32_t* unit_idx = e->pick_map + np;
+        {
+            Scope sc(e, PK_RESIZE, s);
+            frame_map_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(idx, B, T, K, e->pick_map, unit_idx);
+            SASVQA_CUDA_CHECK(cudaGetLastError());
+            count_launch();
+            if ((rc = launch_resize_crop_u8(u8, (long long)nf, H, Wd, e->pick_map, 0, (int)np, e->picked, s))) return rc;
+        }
+        Scope sc(e, PK_GATHER, s);
+        if ((rc = launch_gather_u8(e->picked, unit_idx, (int)np, 1, 1, sampled, s))) return rc;
+    } else if (sampled) {
         Scope sc(e, PK_GATHER, s);
         if (u8) rc = launch_gather_u8(u8, idx, B, T, K, sampled, s);
         else rc = launch_gather_f32(f32, idx, B, T, K, kFrameElems, sampled, s);
@@ -477,10 +517,12 @@ int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
 
 // Host-buffer pipeline: groups of whole clips; H2D (h2d_stream), compute (compute_stream) and
 // D2H (d2h_stream) of consecutive groups overlap through two staging slots.
-int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int K, int W, int32_t* idx_host,
+int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H, int Wd, int K, int W, int32_t* idx_host,
                     int32_t* status_host, float* sampled_host) {
     SASVQA_REQUIRE(e != nullptr && idx_host != nullptr && status_host != nullptr, "null argument");
     SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 1 && W >= -1, "bad B/T/K/W");
+    SASVQA_REQUIRE(H > 0 && Wd > 0, "bad frame size");
+    const size_t frame_bytes = (size_t)H * Wd * 3;
     if (B == 0) return 0;
     if (T == 0) {
         for (int b = 0; b < B; ++b) status_host[b] = SASVQA_STATUS_EMPTY;
@@ -493,7 +535,7 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int K,
     const size_t out_need = sampled_host ? (size_t)group * K * kFrameElems * sizeof(float) : 0;
     int rc;
     for (int i = 0; i < 2; ++i) {
-        if ((rc = grow((void**)&e->stage[i], &e->stage_cap[i], (size_t)group * T * kFrameElems))) return rc;
+        if ((rc = grow((void**)&e->stage[i], &e->stage_cap[i], (size_t)group * T * frame_bytes))) return rc;
         if (out_need && (rc = grow((void**)&e->out_stage[i], &e->out_stage_cap[i], out_need))) return rc;
         if ((rc = grow((void**)&e->idx_stage[i], &e->idx_stage_cap[i], (size_t)group * (K + 1) * sizeof(int32_t))))
             return rc;
@@ -504,8 +546,8 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int K,
         const int b0 = gi * group, nb = std::min(group, B - b0);
         // stage[slot] is free once group gi-2 has finished computing (its gather reads the frames)
         if (gi >= 2) SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->h2d_stream, e->ev_comp[slot], 0));
-        SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->stage[slot], clips + (size_t)b0 * T * kFrameElems,
-                                          (size_t)nb * T * kFrameElems, cudaMemcpyHostToDevice, e->h2d_stream));
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->stage[slot], clips + (size_t)b0 * T * frame_bytes,
+                                          (size_t)nb * T * frame_bytes, cudaMemcpyHostToDevice, e->h2d_stream));
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_in[slot], e->h2d_stream));
         SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->compute_stream, e->ev_in[slot], 0));
         // idx/out staging of this slot is free once group gi-2's results are on the host
@@ -513,7 +555,7 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int K,
         int32_t* d_idx = e->idx_stage[slot];
         int32_t* d_status = d_idx + (size_t)group * K;
         float* d_out = sampled_host ? e->out_stage[slot] : nullptr;
-        if ((rc = mdf_sample_device(e, e->stage[slot], nullptr, nb, T, K, W, d_idx, d_status, nullptr, nullptr, d_out,
+        if ((rc = mdf_sample_device(e, e->stage[slot], nullptr, nb, T, H, Wd, K, W, d_idx, d_status, nullptr, nullptr, d_out,
                                     e->compute_stream)))
             return rc;
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_comp[slot], e->compute_stream));

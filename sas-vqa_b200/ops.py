@@ -86,7 +86,7 @@ class FrameEncoder:
 
     # ---- instrumentation
     PROFILE_KINDS = ("preprocess", "gemm_patch_embed", "pre_layernorm", "layernorm", "gemm_qkv", "attention",
-                     "gemm_out_proj", "gemm_fc1", "gemm_fc2", "pool_norm", "scores", "select", "gather")
+                     "gemm_out_proj", "gemm_fc1", "gemm_fc2", "pool_norm", "scores", "select", "gather", "resize")
 
     def profile_enable(self, on: bool = True) -> None:
         _capi.check(_capi.lib().sasvqa_profile_enable(self.handle, int(on)), "sasvqa_profile_enable")
@@ -124,6 +124,24 @@ class FrameEncoder:
 
     def features_f32(self, frames_chw: torch.Tensor) -> torch.Tensor:
         return self.forward_patches(patchify_f32(frames_chw))
+
+
+# ---- K0
+def resize_crop_u8(frames_hwc: torch.Tensor) -> torch.Tensor:
+    """uint8 ``[..., H, W, 3]`` -> uint8 ``[..., 224, 224, 3]``: the image processor's shortest-edge bicubic
+    resize + centre crop (``prefetch_loader.py:74-75``), bit-exact with the host implementation."""
+    frames_hwc = _need_cuda(frames_hwc, torch.uint8, "frames")
+    if frames_hwc.dim() < 3 or frames_hwc.shape[-1] != 3:
+        raise ValueError(f"frames must be [..., H, W, 3], got {tuple(frames_hwc.shape)}")
+    lead, (H, W) = tuple(frames_hwc.shape[:-3]), frames_hwc.shape[-3:-1]
+    n = 1
+    for d in lead:
+        n *= d
+    out = torch.empty(lead + (IMG, IMG, 3), dtype=torch.uint8, device=frames_hwc.device)
+    with torch.cuda.device(frames_hwc.device):
+        _capi.check(_capi.lib().sasvqa_resize_crop_u8(frames_hwc.data_ptr(), n, int(H), int(W), out.data_ptr(),
+                                                      _stream(frames_hwc)), "sasvqa_resize_crop_u8")
+    return out
 
 
 # ---- K1
@@ -227,7 +245,7 @@ def gather_frames_f32(frames: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 # ---- whole path
 def mdf_sample_device(enc: FrameEncoder, clips: torch.Tensor, K: int, W: int, want_frames: bool = True,
                       want_aux: bool = False) -> dict:
-    """clips: [B, T, 224, 224, 3] uint8 or [B, T, 3, 224, 224] fp32, on the GPU."""
+    """clips: [B, T, H, W, 3] uint8 (any frame size) or [B, T, 3, 224, 224] fp32, on the GPU."""
     if not clips.is_cuda:
         raise _capi.SasvqaError("clips must be a CUDA tensor (use mdf_sample_host for host buffers)")
     clips = clips.contiguous()
@@ -239,24 +257,34 @@ def mdf_sample_device(enc: FrameEncoder, clips: torch.Tensor, K: int, W: int, wa
     feats = torch.empty(B, T, HIDDEN, dtype=torch.float32, device=dev) if want_aux else None
     sampled = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, device=dev) if want_frames else None
     if clips.dtype == torch.uint8:
-        fn, name = _capi.lib().sasvqa_mdf_sample_u8, "sasvqa_mdf_sample_u8"
+        if clips.dim() != 5 or clips.shape[-1] != 3:
+            raise ValueError(f"uint8 clips must be [B, T, H, W, 3], got {tuple(clips.shape)}")
+        H, Wd = int(clips.shape[2]), int(clips.shape[3])
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().sasvqa_mdf_sample_u8_hw(
+                enc.handle, clips.data_ptr(), B, T, H, Wd, int(K), int(W), idx.data_ptr(), status.data_ptr(),
+                _capi.ptr(lcl), _capi.ptr(feats), _capi.ptr(sampled), _stream(clips)), "sasvqa_mdf_sample_u8_hw")
     elif clips.dtype == torch.float32:
-        fn, name = _capi.lib().sasvqa_mdf_sample_f32, "sasvqa_mdf_sample_f32"
+        if tuple(clips.shape[2:]) != (3, IMG, IMG):
+            raise ValueError(f"fp32 clips must be processed frames [B, T, 3, 224, 224], got {tuple(clips.shape)}")
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().sasvqa_mdf_sample_f32(
+                enc.handle, clips.data_ptr(), B, T, int(K), int(W), idx.data_ptr(), status.data_ptr(),
+                _capi.ptr(lcl), _capi.ptr(feats), _capi.ptr(sampled), _stream(clips)), "sasvqa_mdf_sample_f32")
     else:
         raise TypeError(f"clips must be uint8 HWC or float32 CHW, got {clips.dtype}")
-    with torch.cuda.device(dev):
-        _capi.check(fn(enc.handle, clips.data_ptr(), B, T, int(K), int(W), idx.data_ptr(), status.data_ptr(),
-                       _capi.ptr(lcl), _capi.ptr(feats), _capi.ptr(sampled), _stream(clips)), name)
     return dict(indices=idx, status=status, lcl_avg=lcl, feats=feats, frames=sampled)
 
 
 def mdf_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, K: int, W: int, idx_out: torch.Tensor = None,
                     status_out: torch.Tensor = None, frames_out: torch.Tensor = None, want_frames: bool = True) -> dict:
-    """clips_host: [B, T, 224, 224, 3] uint8 in (ideally pinned) host memory.  Results land in host tensors."""
+    """clips_host: [B, T, H, W, 3] uint8 in (ideally pinned) host memory.  Results land in host tensors."""
     if clips_host.is_cuda or clips_host.dtype != torch.uint8:
         raise TypeError("clips_host must be a uint8 CPU tensor")
+    if clips_host.dim() != 5 or clips_host.shape[-1] != 3:
+        raise ValueError(f"clips_host must be [B, T, H, W, 3], got {tuple(clips_host.shape)}")
     clips_host = clips_host.contiguous()
-    B, T = clips_host.shape[0], clips_host.shape[1]
+    B, T, H, Wd = (int(v) for v in clips_host.shape[:4])
     pin = torch.cuda.is_available()
     if idx_out is None:
         idx_out = torch.empty(B, K, dtype=torch.int32, pin_memory=pin)
@@ -265,10 +293,10 @@ def mdf_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, K: int, W: int,
     if frames_out is None and want_frames:
         frames_out = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, pin_memory=pin)
     with torch.cuda.device(enc.device):
-        _capi.check(_capi.lib().sasvqa_mdf_sample_host(enc.handle, clips_host.data_ptr(), B, T, int(K), int(W),
-                                                       idx_out.data_ptr(), status_out.data_ptr(),
-                                                       _capi.ptr(frames_out) if want_frames else None),
-                    "sasvqa_mdf_sample_host")
+        _capi.check(_capi.lib().sasvqa_mdf_sample_host_hw(enc.handle, clips_host.data_ptr(), B, T, H, Wd, int(K), int(W),
+                                                          idx_out.data_ptr(), status_out.data_ptr(),
+                                                          _capi.ptr(frames_out) if want_frames else None),
+                    "sasvqa_mdf_sample_host_hw")
     return dict(indices=idx_out, status=status_out, frames=frames_out if want_frames else None)
 
 

@@ -359,3 +359,40 @@ def test_full_size_properties_c2_like(encoder):
         assert torch.equal(torch.cat([h["indices"] for h in halves]).cpu(), idx)
         want = synth.normalize_frames_reference(clips[3][idx[3].to(DEV).long()])
         assert (res["frames"][3] - want).abs().max().item() <= 2e-6
+
+
+# ------------------------------------------------------------------ K0: resize + centre crop (row f3)
+def test_resize_crop_bit_exact_vs_oracle_and_hf_fixture(golden_dir):
+    from oracle import resize
+    g = _golden(golden_dir, "resize_hf.npz")
+    for h, w in resize.RESIZE_CASES:
+        frames = resize.resize_case_frames(h, w)
+        got = ops.resize_crop_u8(torch.from_numpy(frames).to(DEV)).cpu().numpy()
+        assert np.array_equal(got, g[f"out_{h}x{w}"]), (h, w)             # == the HF image processor's own output
+    # sizes the fixture does not hold (large down-scale, portrait, tiny up-scale, odd sizes; several frames)
+    for h, w, n in [(720, 1280, 2), (640, 360, 3), (64, 48, 2), (251, 333, 5), (1080, 1920, 1)]:
+        rng = np.random.RandomState(h * 3 + w)
+        frames = rng.randint(0, 256, (n, h, w, 3), dtype=np.uint8)
+        got = ops.resize_crop_u8(torch.from_numpy(frames).to(DEV)).cpu().numpy()
+        assert np.array_equal(got, resize.resize_crop_u8(frames)), (h, w)
+    same = torch.randint(0, 256, (3, 224, 224, 3), dtype=torch.uint8, device=DEV)
+    assert torch.equal(ops.resize_crop_u8(same), same)                    # 224x224: resize and crop are identities
+
+
+def test_e2e_non_224_clips_equal_processed_clips(encoder):
+    """Decoded frames of another size go through K0 -> the result must be exactly what the path gives for the
+    clip the host image processor would have produced (oracle resize), on the device and the host entry points."""
+    from oracle import resize
+    T, K, W = 40, 5, 3
+    for h, w in [(240, 320), (300, 226)]:
+        raw = torch.stack([synth.make_clip(70 + b, T, H=h, W=w) for b in range(2)])            # [2, T, h, w, 3]
+        processed = torch.from_numpy(resize.resize_crop_u8(raw.numpy()))                          # [2, T, 224, 224, 3]
+        want = sas.sample_mdf_batch(processed.to(DEV), encoder, K, W, want_aux=True)
+        got = sas.sample_mdf_batch(raw.to(DEV), encoder, K, W, want_aux=True)
+        host = sas.sample_mdf_host(raw.pin_memory(), encoder, K, W)
+        for key in ("indices", "status", "frames", "feats", "lcl_avg"):
+            assert torch.equal(got[key], want[key]), (key, h, w)
+        for key in ("indices", "status", "frames"):
+            assert torch.equal(host[key], want[key].cpu()), (key, h, w)
+        assert torch.equal(got["frames"][1].cpu(),
+                           synth.normalize_frames_reference(processed[1][got["indices"][1].cpu().long()]))

@@ -174,3 +174,34 @@ def test_live_reference_agrees_on_fresh_random_cases():
     assert checked >= 80
     frames = torch.arange(100, dtype=torch.float32).view(100, 1)
     assert ref_uni(frames, K=8).reshape(-1).long().tolist() == mdf.uniform_indices(100, 8)
+
+
+# ------------------------------------------------------------------ K0 oracle: resize + centre crop
+def test_resize_restatement_matches_hf_processor_fixture(golden_dir):
+    """oracle/resize.py == the installed HF CLIPImageProcessor (fixture written by oracle/make_golden.py)."""
+    from oracle import resize
+    g = _load(golden_dir, "resize_hf.npz")
+    assert [tuple(c) for c in g["cases"].tolist()] == resize.RESIZE_CASES
+    for h, w in resize.RESIZE_CASES:
+        frames = resize.resize_case_frames(h, w)
+        got = resize.resize_crop_u8(frames)
+        assert got.shape == (2, 224, 224, 3) and got.dtype == np.uint8
+        assert np.array_equal(got, g[f"out_{h}x{w}"]), (h, w)
+        px = vit.image_processor_224(torch.from_numpy(got))            # rescale + normalise of the cropped frame
+        assert np.abs(px[:, :, ::37, ::41].numpy() - g[f"pixel_probe_{h}x{w}"]).max() <= 1e-6
+
+
+def test_resize_restatement_matches_torch_cpu_kernel_live():
+    """Live pin against the third-party code itself: torch's CPU uint8 anti-aliased bicubic resampler
+    (what torchvision's resize calls for the reference's host image processor)."""
+    from oracle import resize
+    for h, w in [(250, 333), (224, 300), (500, 224), (97, 131), (448, 448)]:
+        rng = np.random.RandomState(h + w)
+        img = rng.randint(0, 256, (1, h, w, 3), dtype=np.uint8)
+        oh, ow = resize.output_size(h, w)
+        ref = torch.nn.functional.interpolate(torch.from_numpy(img).permute(0, 3, 1, 2), size=(oh, ow), mode="bicubic",
+                                              antialias=True, align_corners=False).permute(0, 2, 3, 1).numpy()
+        top, left = int((oh - 224) / 2.0), int((ow - 224) / 2.0)
+        assert np.array_equal(resize.resize_crop_u8(img), ref[:, top:top + 224, left:left + 224]), (h, w)
+    same = np.random.RandomState(1).randint(0, 256, (2, 224, 224, 3), dtype=np.uint8)
+    assert np.array_equal(resize.resize_crop_u8(same), same)
