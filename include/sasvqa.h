@@ -12,7 +12,8 @@
  * makes the copies asynchronous).  `stream` is a cudaStream_t passed as void* (NULL = default
  * stream); device-pointer entry points are asynchronous on it, host-pointer entry points return
  * after the results are in host memory.  Outputs are caller-allocated.  bf16 buffers are passed
- * as uint16_t*.  Frames are 224x224 (ViT-B/16 input of the reference's GitVisionModel).
+ * as uint16_t*.  Frames are 224x224 (ViT-B/16 input of the reference's GitVisionModel) unless an entry
+ * point takes H and W (decoded frames of any size: K0 resizes and crops them as the image processor does).
  */
 #ifndef SASVQA_H
 #define SASVQA_H
@@ -89,6 +90,16 @@ int sasvqa_mdf_select(const float* lcl_avg_dev, int B, int T, int K, int W, int3
 /* ---- K4c: MIF strided top-K (gen_sample.py:87-88) --------------------------------------------
  * idx[b, :] = ds_rate * topk(scores[b, ::ds_rate], K), best first. */
 int sasvqa_topk_strided(const float* scores_dev, int B, int T, int ds_rate, int K, int32_t* idx_dev, void* stream);
+
+/* ---- MIF relevance in embedding space (BASELINE config 3) --------------------------------------
+ * scores[b, t] = <feats[b, t], q[b]>: feats [B, T, 768], one question embedding q [B, 768] per clip.
+ * (The reference scores frames with a caption cross-encoder, gen_sample.py:80-83; only the top-K that
+ * follows is pinned by it.)  Whole path: clips [B, T, H, W, 3] uint8 -> encoder -> scores -> strided top-K
+ * (-> optional gather of the K picks); optional outputs may be NULL. */
+int sasvqa_mif_scores(const float* feats_dev, const float* q_dev, int B, int T, float* scores_dev, void* stream);
+int sasvqa_mif_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips_hwc_dev, int B, int T, int H, int W,
+                            const float* q_dev, int K, int ds_rate, int32_t* idx_dev, float* scores_or_null_dev,
+                            float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
 
 /* ---- K5: gather the selected frames as normalised fp32 rows (utils.py:94, extract_features.py:96)
  * out [B, K, 3*224*224]; out-of-range indices give zero rows. */

@@ -177,3 +177,10 @@ def mif_select(scores, K: int, ds_rate: int = 1) -> list[int]:
     indices, best first (never sorted by index)."""
     v = np.asarray(scores, dtype=np.float32)[::ds_rate]
     return [i * ds_rate for i in topk_lowest_index(v, K)]
+
+
+def mif_scores(feats: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """Embedding-space relevance of BASELINE config 3 (no reference counterpart -- the
+    reference's relevance model is the caption cross-encoder of gen_sample.py:80-83):
+    scores[t] = <feats[t], q>, fp32."""
+    return feats.float() @ q.float()

@@ -14,10 +14,11 @@ from .sampler import (  # noqa: F401
     sample_frames_uniform,
     sample_mdf_batch,
     sample_mdf_host,
+    sample_mif_batch,
     sample_representative_frames,
 )
 
 __all__ = [
     "FrameEncoder", "SasvqaError", "mif_select", "sample_frame_indices", "sample_frames_uniform",
-    "sample_mdf_batch", "sample_mdf_host", "sample_representative_frames", "synth",
+    "sample_mdf_batch", "sample_mdf_host", "sample_mif_batch", "sample_representative_frames", "synth",
 ]

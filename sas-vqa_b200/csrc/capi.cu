@@ -21,6 +21,8 @@ int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, c
 int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int, int, int32_t*, int32_t*,
                       float*, float*, float*, cudaStream_t);
 int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int, int, int32_t*, int32_t*, float*);
+int mif_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, const float*, int, int, int32_t*,
+                      float*, float*, float*, cudaStream_t);
 
 }  // namespace sasvqa
 
@@ -77,6 +79,17 @@ int sasvqa_topk_strided(const float* scores, int B, int T, int ds_rate, int K, i
     SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 0, "bad B/T/K");
     SASVQA_REQUIRE(B == 0 || K == 0 || (scores && idx), "null argument");
     return launch_topk_strided(scores, B, T, ds_rate, K, idx, nullptr, S(stream));
+}
+
+int sasvqa_mif_scores(const float* feats, const float* q, int B, int T, float* scores, void* stream) {
+    SASVQA_REQUIRE(B >= 0 && T >= 0, "bad B/T");
+    SASVQA_REQUIRE(B == 0 || T == 0 || (feats && q && scores), "null argument");
+    return launch_mif_scores(feats, q, B, T, scores, S(stream));
+}
+int sasvqa_mif_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips, int B, int T, int H, int Wd, const float* q, int K,
+                            int ds_rate, int32_t* idx, float* scores, float* feats, float* sampled, void* stream) {
+    SASVQA_REQUIRE(B == 0 || clips != nullptr, "null clips");
+    return mif_sample_device(enc, clips, nullptr, B, T, H, Wd, q, K, ds_rate, idx, scores, feats, sampled, S(stream));
 }
 
 int sasvqa_gather_frames_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, void* stream) {

@@ -94,6 +94,7 @@ int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv
 int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s);
 int launch_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status,
                       cudaStream_t s);
+int launch_mif_scores(const float* feats, const float* q, int B, int T, float* scores, cudaStream_t s);
 int launch_topk_strided(const float* scores, int B, int T, int ds_rate, int K, int32_t* idx,
                         const int32_t* only_if_status, cudaStream_t s);
 int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s);

@@ -455,6 +455,32 @@ static int encode_frames(SasvqaEncoder* e, const uint8_t* u8, const float* f32, 
     return 0;
 }
 
+// K5 for any frame size: the sampled rows are the image processor's output for the K picks of every clip
+static int gather_picks(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int H, int Wd, int K,
+                        const int32_t* idx, float* sampled, cudaStream_t s) {
+    int rc = 0;
+    const size_t nf = (size_t)B * T;
+    if (u8 && (H != kImg || Wd != kImg)) {                       // resize only the picks, then gather
+        const size_t np = (size_t)B * K;
+        if ((rc = grow((void**)&e->picked, &e->picked_cap, np * kFrameElems))) return rc;
+        if ((rc = grow((void**)&e->pick_map, &e->pick_map_cap, 2 * np * sizeof(int32_t)))) return rc;
+        int32_t* unit_idx = e->pick_map + np;
+        {
+            Scope sc(e, PK_RESIZE, s);
+            frame_map_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(idx, B, T, K, e->pick_map, unit_idx);
+            SASVQA_CUDA_CHECK(cudaGetLastError());
+            count_launch();
+            if ((rc = launch_resize_crop_u8(u8, (long long)nf, H, Wd, e->pick_map, 0, (int)np, e->picked, s))) return rc;
+        }
+        Scope sc(e, PK_GATHER, s);
+        return launch_gather_u8(e->picked, unit_idx, (int)np, 1, 1, sampled, s);
+    }
+    Scope sc(e, PK_GATHER, s);
+    if (u8) rc = launch_gather_u8(u8, idx, B, T, K, sampled, s);
+    else rc = launch_gather_f32(f32, idx, B, T, K, kFrameElems, sampled, s);
+    return rc;
+}
+
 int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int H, int Wd, int K, int W,
                       int32_t* idx, int32_t* status, float* lcl_out, float* feats_out, float* sampled, cudaStream_t s) {
     SASVQA_REQUIRE(e != nullptr && idx != nullptr && status != nullptr, "null argument");
@@ -492,27 +518,42 @@ int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
         Scope sc(e, PK_SELECT, s);
         if ((rc = launch_mdf_select(lcl, B, T, K, W, idx, status, s))) return rc;
     }
-    if (sampled && u8 && (H != kImg || Wd != kImg)) {           // resize only the K picks of every clip, then gather
-        const size_t np = (size_t)B * K;
-        if ((rc = grow((void**)&e->picked, &e->picked_cap, np * kFrameElems))) return rc;
-        if ((rc = grow((void**)&e->pick_map, &e->pick_map_cap, 2 * np * sizeof(int32_t)))) return rc;
-        int32_t* unit_idx = e->pick_map + np;
-        {
-            Scope sc(e, PK_RESIZE, s);
-            frame_map_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(idx, B, T, K, e->pick_map, unit_idx);
-            SASVQA_CUDA_CHECK(cudaGetLastError());
-            count_launch();
-            if ((rc = launch_resize_crop_u8(u8, (long long)nf, H, Wd, e->pick_map, 0, (int)np, e->picked, s))) return rc;
-        }
-        Scope sc(e, PK_GATHER, s);
-        if ((rc = launch_gather_u8(e->picked, unit_idx, (int)np, 1, 1, sampled, s))) return rc;
-    } else if (sampled) {
-        Scope sc(e, PK_GATHER, s);
-        if (u8) rc = launch_gather_u8(u8, idx, B, T, K, sampled, s);
-        else rc = launch_gather_f32(f32, idx, B, T, K, kFrameElems, sampled, s);
-        if (rc) return rc;
-    }
+    if (sampled && (rc = gather_picks(e, u8, f32, B, T, H, Wd, K, idx, sampled, s))) return rc;
     return 0;
+}
+
+// MIF with embedding-space relevance (BASELINE config 3): encode -> <feat, q> -> strided top-K -> gather.
+int mif_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int H, int Wd, const float* q,
+                      int K, int ds_rate, int32_t* idx, float* scores_out, float* feats_out, float* sampled,
+                      cudaStream_t s) {
+    SASVQA_REQUIRE(e != nullptr && idx != nullptr && q != nullptr, "null argument");
+    SASVQA_REQUIRE(B >= 0 && T >= 1 && K >= 1 && ds_rate >= 1, "bad B/T/K/ds_rate");
+    SASVQA_REQUIRE(H > 0 && Wd > 0, "bad frame size");
+    SASVQA_REQUIRE(u8 != nullptr || (H == kImg && Wd == kImg), "fp32 frames are already processed: they must be 224x224");
+    SASVQA_REQUIRE(K <= (T + ds_rate - 1) / ds_rate, "selected index k out of range");
+    if (B == 0) return 0;
+    int rc;
+    const size_t nf = (size_t)B * T;
+    float* feats = feats_out;
+    if (!feats) {
+        if ((rc = grow((void**)&e->feats, &e->feats_cap, nf * kHidden * sizeof(float)))) return rc;
+        feats = e->feats;
+    }
+    float* scores = scores_out;
+    if (!scores) {
+        if ((rc = grow((void**)&e->lcl, &e->lcl_cap, nf * sizeof(float)))) return rc;
+        scores = e->lcl;
+    }
+    if ((rc = encode_frames(e, u8, f32, (long long)nf, H, Wd, feats, s))) return rc;
+    {
+        Scope sc(e, PK_SCORES, s);
+        if ((rc = launch_mif_scores(feats, q, B, T, scores, s))) return rc;
+    }
+    {
+        Scope sc(e, PK_SELECT, s);
+        if ((rc = launch_topk_strided(scores, B, T, ds_rate, K, idx, nullptr, s))) return rc;
+    }
+    return sampled ? gather_picks(e, u8, f32, B, T, H, Wd, K, idx, sampled, s) : 0;
 }
 
 // Host-buffer pipeline: groups of whole clips; H2D (h2d_stream), compute (compute_stream) and

@@ -50,6 +50,34 @@ __global__ void __launch_bounds__(256) mdf_scores_kernel(const float* __restrict
     if (lane == 0) lcl[wid] = __fdiv_rn(__fsub_rn(window, 1.0f), (float)(2 * W - 1));
 }
 
+// ---------------------------------------------------------------------------------------------
+// MIF relevance (BASELINE config 3): scores[b, t] = <feats[b, t], q[b]> with one question embedding per
+// clip.  (The reference scores frames with a BERT cross-encoder over generated captions,
+// src/preprocessing/gen_sample.py:80-83 -- out of scope; this is the embedding-space surrogate the
+// north star names.  What the reference pins is the strided top-K that follows, gen_sample.py:87-88.)
+// One warp per (clip, frame) row: 3 KB of features streamed once with 16-byte loads; q stays in L1/L2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mif_scores_kernel(const float* __restrict__ feats, const float* __restrict__ q, int B,
+                                                          int T, float* __restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (long long)B * T) return;
+    const long long b = wid / T;
+    const float4* f = reinterpret_cast<const float4*>(feats + wid * kHidden);
+    const float4* qq = reinterpret_cast<const float4*>(q + b * kHidden);
+    float d = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float4 v = __ldg(f + lane + 32 * j), w = __ldg(qq + lane + 32 * j);
+        d = fmaf(v.x, w.x, d);
+        d = fmaf(v.y, w.y, d);
+        d = fmaf(v.z, w.z, d);
+        d = fmaf(v.w, w.w, d);
+    }
+    d = warp_sum(d);
+    if (lane == 0) scores[wid] = d;
+}
+
 // Optional full Gram (debug / inspection output of sasvqa_mdf_scores): S[b] = F_b F_b^T.
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ feats, int T, float* __restrict__ gram) {
     __shared__ float fa[16][33], fb[16][33];
@@ -283,6 +311,17 @@ int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, f
         SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     }
+    return 0;
+}
+
+int launch_mif_scores(const float* feats, const float* q, int B, int T, float* scores, cudaStream_t s) {
+    if (B == 0 || T == 0) return 0;
+    SASVQA_REQUIRE((((uintptr_t)feats | (uintptr_t)q) & 15) == 0, "feats and q must be 16-byte aligned");
+    const long long blocks = ((long long)B * T + 7) / 8;
+    SASVQA_REQUIRE(blocks < 2147483647LL, "too many frames for one scores launch");
+    mif_scores_kernel<<<(unsigned)blocks, 256, 0, s>>>(feats, q, B, T, scores);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
     return 0;
 }
 

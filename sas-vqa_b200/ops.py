@@ -300,6 +300,42 @@ def mdf_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, K: int, W: int,
     return dict(indices=idx_out, status=status_out, frames=frames_out if want_frames else None)
 
 
+def mif_scores(feats: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """feats [B, T, 768] fp32, q [B, 768] fp32 -> relevance scores [B, T] = <feats[b, t], q[b]>."""
+    feats = _need_cuda(feats, torch.float32, "feats")
+    q = _need_cuda(q, torch.float32, "q")
+    B, T = feats.shape[0], feats.shape[1]
+    if tuple(q.shape) != (B, HIDDEN) or feats.shape[2] != HIDDEN:
+        raise ValueError(f"need feats [B, T, 768] and q [B, 768], got {tuple(feats.shape)} and {tuple(q.shape)}")
+    out = torch.empty(B, T, dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _capi.check(_capi.lib().sasvqa_mif_scores(feats.data_ptr(), q.data_ptr(), B, T, out.data_ptr(), _stream(feats)),
+                    "sasvqa_mif_scores")
+    return out
+
+
+def mif_sample_device(enc: FrameEncoder, clips: torch.Tensor, q: torch.Tensor, K: int, ds_rate: int = 1,
+                      want_frames: bool = False, want_aux: bool = False) -> dict:
+    """clips [B, T, H, W, 3] uint8 on the GPU, q [B, 768] fp32 question embeddings."""
+    clips = _need_cuda(clips, torch.uint8, "clips")
+    q = _need_cuda(q, torch.float32, "q")
+    if clips.dim() != 5 or clips.shape[-1] != 3:
+        raise ValueError(f"clips must be [B, T, H, W, 3], got {tuple(clips.shape)}")
+    B, T, H, Wd = (int(v) for v in clips.shape[:4])
+    if tuple(q.shape) != (B, HIDDEN):
+        raise ValueError(f"q must be [B, 768], got {tuple(q.shape)}")
+    dev = clips.device
+    idx = torch.empty(B, K, dtype=torch.int32, device=dev)
+    scores = torch.empty(B, T, dtype=torch.float32, device=dev) if want_aux else None
+    feats = torch.empty(B, T, HIDDEN, dtype=torch.float32, device=dev) if want_aux else None
+    sampled = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, device=dev) if want_frames else None
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().sasvqa_mif_sample_u8_hw(
+            enc.handle, clips.data_ptr(), B, T, H, Wd, q.data_ptr(), int(K), int(ds_rate), idx.data_ptr(),
+            _capi.ptr(scores), _capi.ptr(feats), _capi.ptr(sampled), _stream(clips)), "sasvqa_mif_sample_u8_hw")
+    return dict(indices=idx, scores=scores, feats=feats, frames=sampled)
+
+
 def launch_count() -> int:
     return int(_capi.lib().sasvqa_launch_count())
 

@@ -128,3 +128,14 @@ def mif_select(scores: torch.Tensor, K: int, ds_rate: int = 1):
         s = s.cuda()
     idx = ops.topk_strided(s.float(), K, ds_rate)
     return idx.cpu().tolist() if scores.dim() == 1 else idx
+
+
+def sample_mif_batch(clips: torch.Tensor, model, question_embeds: torch.Tensor, K: int = 8, ds_rate: int = 1,
+                     want_frames: bool = False, want_aux: bool = False) -> dict:
+    """Batched MIF with embedding-space relevance (BASELINE config 3): every frame of ``clips``
+    ([B, T, H, W, 3] uint8 on the GPU) is encoded, scored against its clip's question embedding
+    (``question_embeds`` [B, 768]) and the K best of every ``ds_rate``-th frame are returned best first --
+    the selection rule of gen_sample.py:87-88.  dict(indices int32 [B, K], scores, feats, frames)."""
+    enc = as_frame_encoder(model)
+    return ops.mif_sample_device(enc, clips, question_embeds.to(device=clips.device, dtype=torch.float32), K, ds_rate,
+                                 want_frames=want_frames, want_aux=want_aux)

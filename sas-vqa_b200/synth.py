@@ -133,3 +133,15 @@ def random_encoder_state_dict(seed: int = REF_SEED, bf16_exact: bool = True) -> 
             t = t.to(torch.bfloat16).to(torch.float32)
         sd[name] = t.contiguous()
     return sd
+
+
+def question_embeddings(clip_ids, seed: int = REF_SEED, device="cpu") -> torch.Tensor:
+    """Synthetic question text embeddings for the MIF workload (BASELINE config 3): one unit vector
+    ``normalize(randn(768))`` per clip from ``Generator(seed + clip_id)`` -- the embedding-space surrogate of
+    SURVEY.md 8(d); the reference's own relevance model (a caption cross-encoder) is out of scope."""
+    rows = []
+    for cid in clip_ids:
+        g = torch.Generator()
+        g.manual_seed(seed + int(cid))
+        rows.append(torch.nn.functional.normalize(torch.randn(HIDDEN, generator=g), dim=0))
+    return torch.stack(rows).to(device) if rows else torch.zeros(0, HIDDEN, device=device)

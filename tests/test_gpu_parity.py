@@ -396,3 +396,62 @@ def test_e2e_non_224_clips_equal_processed_clips(encoder):
             assert torch.equal(host[key], want[key].cpu()), (key, h, w)
         assert torch.equal(got["frames"][1].cpu(),
                            synth.normalize_frames_reference(processed[1][got["indices"][1].cpu().long()]))
+
+
+# ------------------------------------------------------------------ MIF, BASELINE config 3 (embedding relevance)
+def test_mif_scores_and_selection_vs_oracle():
+    g = torch.Generator().manual_seed(5)
+    B, T = 6, 128
+    feats = torch.nn.functional.normalize(torch.randn(B, T, 768, generator=g), dim=-1)
+    q = synth.question_embeddings(range(B))
+    got = ops.mif_scores(feats.to(DEV), q.to(DEV)).cpu()
+    for b in range(B):
+        want = mdf.mif_scores(feats[b], q[b])
+        assert (got[b] - want).abs().max().item() <= 1e-5
+        for K, ds in [(8, 1), (8, 2), (5, 3), (1, 1)]:                       # selection on the GPU's own scores: exact
+            idx = ops.topk_strided(got[b:b + 1].to(DEV), K, ds)[0].cpu().tolist()
+            assert idx == mdf.mif_select(got[b].numpy(), K, ds)
+
+
+def test_mif_e2e_c3_like(encoder, vit_oracle):
+    """clips -> encoder -> <feat, q> -> strided top-K, against the fp32 oracle chain on the same clips."""
+    T, K = 32, 8
+    ids = [40, 41]
+    clips = torch.stack([synth.make_clip(c, T) for c in ids])
+    q = synth.question_embeddings(ids)
+    for ds in (1, 2):
+        res = sas.sample_mif_batch(clips.to(DEV), encoder, q, K, ds, want_frames=True, want_aux=True)
+        for b in range(len(ids)):
+            frames = vit.image_processor_224(clips[b])
+            feats = vit_oracle.features(frames)
+            want_scores = mdf.mif_scores(feats, q[b])
+            got_scores = res["scores"][b].cpu()
+            eps = (got_scores - want_scores).abs().max().item()
+            assert eps <= 1e-3                                                # bf16 encoder vs fp32, as for the Gram
+            got = res["indices"][b].cpu().tolist()
+            assert got == mdf.mif_select(got_scores.numpy(), K, ds)           # exact on its own scores
+            assert_same_or_tied(got, mdf.mif_select(want_scores.numpy(), K, ds), want_scores, eps=2 * eps)
+            assert all(i % ds == 0 for i in got)
+            assert torch.equal(res["frames"][b].cpu(), frames[torch.tensor(got)])
+    with pytest.raises(sas.SasvqaError):
+        sas.sample_mif_batch(clips.to(DEV), encoder, q, 20, 2)                # K > ceil(T / ds_rate): topk raises
+
+
+def test_full_size_properties_c4_long_video(encoder):
+    """BASELINE config 4 shape (T=512, K=32, W=8): spacing rule / first pick / chunk invariance on long clips."""
+    B, T, K, W = 2, 512, 32, 8
+    clips = synth.make_clips(range(300, 300 + B), T, device=DEV)
+    res = sas.sample_mdf_batch(clips, encoder, K, W, want_aux=True)
+    idx, st, lcl = res["indices"].cpu(), res["status"].cpu(), res["lcl_avg"].cpu()
+    for b in range(B):
+        picks = idx[b].tolist()
+        assert len(set(picks)) == K and min(picks) >= 0 and max(picks) < T
+        assert torch.all(lcl[b][:W] == 0) and torch.all(lcl[b][T - W:] == 0)
+        if st[b] == 0:
+            assert picks[0] == int(lcl[b].argmax())
+            assert min(abs(p - r) for i, p in enumerate(picks) for r in picks[:i]) >= W
+        want, status = mdf.mdf_select(lcl[b], K, W)                         # oracle selection on the GPU's scores
+        assert status == int(st[b])
+        assert_same_or_tied(picks, want, lcl[b])
+    one = sas.sample_mdf_batch(clips[1:2], encoder, K, W)
+    assert torch.equal(one["indices"].cpu(), idx[1:2])
