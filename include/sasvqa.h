@@ -134,13 +134,27 @@ int sasvqa_mdf_sample_host(SasvqaEncoder* enc, const uint8_t* clips_hwc_host, in
 int sasvqa_mdf_sample_host_hw(SasvqaEncoder* enc, const uint8_t* clips_hwc_host, int B, int T, int H, int W, int K,
                               int Wwin, int32_t* idx_host, int32_t* status_host, float* sampled_or_null_host);
 
+/* ---- downstream consumer: visual tokens of the sampled frames (src/modeling/modeling.py:76-95) ----
+ * MyGitModel.forward runs `image_encoder(frame).last_hidden_state` frame by frame, concatenates along the
+ * sequence and applies `visual_projection` (HF GitProjection: Linear(768,768) + LayerNorm).  The image
+ * encoder is the sampler's encoder: frames [n, 3, 224, 224] fp32 (rows of "sampled_frames") or uint8 HWC ->
+ * tokens [n * 197, 768] fp32; project == 0 stops at last_hidden_state.  Projection weights are host fp32:
+ * visual_projection.0.weight [768, 768], .0.bias, .1.weight, .1.bias. */
+int sasvqa_encoder_set_projection(SasvqaEncoder* enc, const float* weight_host, const float* bias_host,
+                                  const float* ln_weight_host, const float* ln_bias_host);
+int sasvqa_visual_tokens_f32(SasvqaEncoder* enc, const float* frames_chw_dev, int n_frames, int project,
+                             float* tokens_dev, void* stream);
+int sasvqa_visual_tokens_u8(SasvqaEncoder* enc, const uint8_t* frames_hwc_dev, int n_frames, int project,
+                            float* tokens_dev, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------
  * sasvqa_launch_count: kernels launched by this library in this process so far.
  * Profiling: when enabled, CUDA-event pairs bracket every stage launch on its stream;
  * sasvqa_profile_read synchronises, sums milliseconds and scope counts per stage kind and resets.
  * Kinds: 0 preprocess, 1 gemm_patch_embed, 2 pre_layernorm, 3 layernorm, 4 gemm_qkv, 5 attention,
- * 6 gemm_out_proj, 7 gemm_fc1, 8 gemm_fc2, 9 pool_norm, 10 scores, 11 select, 12 gather, 13 resize. */
-#define SASVQA_PROFILE_KINDS 14
+ * 6 gemm_out_proj, 7 gemm_fc1, 8 gemm_fc2, 9 pool_norm, 10 scores, 11 select, 12 gather, 13 resize,
+ * 14 projection. */
+#define SASVQA_PROFILE_KINDS 15
 int64_t sasvqa_launch_count(void);
 int sasvqa_profile_enable(SasvqaEncoder* enc, int on);
 int sasvqa_profile_read(SasvqaEncoder* enc, double* ms_out, int64_t* scopes_out, int n_kinds);

@@ -182,6 +182,27 @@ def gen_encoder_and_e2e():
     np.savez_compressed(os.path.join(GOLD, "mdf_e2e_hf.npz"), **out)
 
 
+def gen_visual_tokens():
+    """HF GitVisionModel + HF GitProjection (the modules the reference's MyGitModel.forward calls,
+    src/modeling/modeling.py:76-95) on 2 clips x 2 frames with the seeded weights."""
+    from transformers import GitConfig
+    from transformers.models.git.modeling_git import GitProjection
+    sd = synth.random_encoder_state_dict(synth.REF_SEED)
+    psd = synth.random_projection_state_dict()
+    hf = vit.hf_model_from_state_dict(sd)
+    proj = GitProjection(GitConfig()).eval()
+    proj.load_state_dict(psd)
+    frames = torch.stack([vit.image_processor_224(synth.make_clip(c, 2)) for c in (50, 51)])      # [2, 2, 3, 224, 224]
+    with torch.no_grad():
+        hidden = torch.cat([hf(frames[:, f]).last_hidden_state for f in range(frames.shape[1])], dim=1)
+        tokens = proj(hidden)
+        mine = vit.visual_tokens(frames, vit.VitOracle(sd), psd)
+    print("visual tokens: restatement vs HF max |diff|:", float((mine - tokens).abs().max()))
+    np.savez_compressed(os.path.join(GOLD, "visual_tokens_hf.npz"), clip_ids=np.asarray([50, 51]), T=np.int64(2),
+                        hidden_probe=hidden[:, ::29, ::48].numpy(), tokens_probe=tokens[:, ::29, ::48].numpy(),
+                        tokens_rowsum=tokens.double().sum(dim=-1).numpy())
+
+
 def gen_resize():
     """The installed HF CLIPImageProcessor (the reference's `self.processor`, prefetch_loader.py:74) on frames
     that need the shortest-edge bicubic resize + centre crop.  Its fp32 output is inverted to the uint8 image
@@ -210,6 +231,9 @@ if __name__ == "__main__":
     if "--resize-only" in sys.argv:
         gen_resize()
         sys.exit(0)
+    if "--visual-only" in sys.argv:
+        gen_visual_tokens()
+        sys.exit(0)
     assert ref_loader.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
@@ -217,3 +241,4 @@ if __name__ == "__main__":
     gen_misc()
     gen_encoder_and_e2e()
     gen_resize()
+    gen_visual_tokens()

@@ -105,3 +105,19 @@ def hf_model_from_state_dict(state_dict: dict):
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not unexpected and all("position_ids" in m for m in missing), (missing, unexpected)
     return model.eval()
+
+
+def visual_tokens(frames: torch.Tensor, encoder, projection_sd: dict | None) -> torch.Tensor:
+    """The visual side of the reference's downstream forward, ``src/modeling/modeling.py:76-95``
+    (``MyGitModel.forward``, 5-D ``pixel_values``): for every frame index ``image_encoder(pixel_values[:, f])
+    .last_hidden_state``, concatenated along the sequence (the temporal embedding is commented out there,
+    ``:87``), then ``visual_projection`` = HF ``GitProjection`` (``transformers/models/git/modeling_git.py``:
+    ``nn.Sequential(nn.Linear(768, hidden), nn.LayerNorm(hidden, eps=1e-5))``).
+    frames [B, K, 3, 224, 224] fp32 -> [B, K * 197, 768]; ``projection_sd`` None stops before the projection."""
+    feats = [encoder(frames[:, f]).last_hidden_state for f in range(frames.shape[1])]
+    x = torch.cat(feats, dim=1)
+    if projection_sd is None:
+        return x
+    x = F.linear(x, projection_sd["visual_projection.0.weight"], projection_sd["visual_projection.0.bias"])
+    return F.layer_norm(x, (HIDDEN,), projection_sd["visual_projection.1.weight"],
+                        projection_sd["visual_projection.1.bias"], EPS)

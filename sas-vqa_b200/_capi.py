@@ -28,6 +28,9 @@ SIGNATURES = {
     "sasvqa_mdf_scores": (c_int, [_p, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_mdf_select": (c_int, [_p, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_topk_strided": (c_int, [_p, c_int, c_int, c_int, c_int, _p, _p]),
+    "sasvqa_encoder_set_projection": (c_int, [_p, _p, _p, _p, _p]),
+    "sasvqa_visual_tokens_f32": (c_int, [_p, _p, c_int, c_int, _p, _p]),
+    "sasvqa_visual_tokens_u8": (c_int, [_p, _p, c_int, c_int, _p, _p]),
     "sasvqa_mif_scores": (c_int, [_p, _p, c_int, c_int, _p, _p]),
     "sasvqa_mif_sample_u8_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, c_int, c_int, _p, _p, _p, _p, _p]),
     "sasvqa_gather_frames_u8": (c_int, [_p, _p, c_int, c_int, c_int, _p, _p]),

@@ -21,6 +21,8 @@ int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, c
 int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int, int, int32_t*, int32_t*,
                       float*, float*, float*, cudaStream_t);
 int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int, int, int32_t*, int32_t*, float*);
+int encoder_set_projection(SasvqaEncoder*, const float*, const float*, const float*, const float*);
+int visual_tokens(SasvqaEncoder*, const uint8_t*, const float*, int, int, float*, cudaStream_t);
 int mif_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, const float*, int, int, int32_t*,
                       float*, float*, float*, cudaStream_t);
 
@@ -79,6 +81,16 @@ int sasvqa_topk_strided(const float* scores, int B, int T, int ds_rate, int K, i
     SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 0, "bad B/T/K");
     SASVQA_REQUIRE(B == 0 || K == 0 || (scores && idx), "null argument");
     return launch_topk_strided(scores, B, T, ds_rate, K, idx, nullptr, S(stream));
+}
+
+int sasvqa_encoder_set_projection(SasvqaEncoder* enc, const float* w, const float* b, const float* ln_g, const float* ln_b) {
+    return encoder_set_projection(enc, w, b, ln_g, ln_b);
+}
+int sasvqa_visual_tokens_f32(SasvqaEncoder* enc, const float* frames, int n_frames, int project, float* tokens, void* stream) {
+    return visual_tokens(enc, nullptr, frames, n_frames, project, tokens, S(stream));
+}
+int sasvqa_visual_tokens_u8(SasvqaEncoder* enc, const uint8_t* frames, int n_frames, int project, float* tokens, void* stream) {
+    return visual_tokens(enc, frames, nullptr, n_frames, project, tokens, S(stream));
 }
 
 int sasvqa_mif_scores(const float* feats, const float* q, int B, int T, float* scores, void* stream) {

@@ -84,6 +84,8 @@ int launch_pre_layernorm(float* x, int n_frames, const float* cls_pos0, const fl
                          cudaStream_t s);
 int launch_layernorm_bf16(const float* x, __nv_bfloat16* h, int rows, const float* gamma, const float* beta,
                           cudaStream_t s);
+int launch_layernorm_f32(const float* x, float* out, long long rows, const float* gamma, const float* beta,
+                         cudaStream_t s);
 int launch_pool_norm(const float* x, int n_frames, const float* gamma, const float* beta, float* feats,
                      cudaStream_t s);
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, cudaStream_t s);   // mma.sync check kernel

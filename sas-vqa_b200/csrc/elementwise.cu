@@ -135,6 +135,23 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
     }
 }
 
+// fp32 -> fp32 LayerNorm (the LayerNorm of GIT's visual projection, modeling_git.py GitProjection); out may alias x.
+__global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* x, float* out, long long rows,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * warps_per_block) {
+        RowRegs r;
+        row_load(x + row * kHidden, lane, r);
+        row_normalize(r, lane, gamma, beta);
+        float4* dst = reinterpret_cast<float4*>(out + row * kHidden);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dst[lane + 32 * j] = r.v[j];
+    }
+}
+
 // pre_layrnorm (HF modeling_git.py:742), in place on the fp32 stream.  Token 0 of every frame is
 // the class token: its input is class_embedding + position_embedding[0] (precomputed), the other
 // 196 rows were written by the patch-embedding GEMM epilogue.
@@ -299,6 +316,15 @@ int launch_layernorm_bf16(const float* x, __nv_bfloat16* h, int rows, const floa
                           cudaStream_t s) {
     if (rows == 0) return 0;
     layernorm_bf16_kernel<<<grid_for(rows, 8), 256, 0, s>>>(x, h, rows, gamma, beta);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_layernorm_f32(const float* x, float* out, long long rows, const float* gamma, const float* beta,
+                         cudaStream_t s) {
+    if (rows == 0) return 0;
+    layernorm_f32_kernel<<<grid_for(rows, 8), 256, 0, s>>>(x, out, rows, gamma, beta);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -43,7 +43,7 @@ __global__ void frame_map_kernel(const int32_t* idx, int B, int T, int K, int32_
 // profiling scopes (bench.py roofline): CUDA-event pairs around each stage's launches
 enum ProfKind {
     PK_PREPROCESS = 0, PK_GEMM_PATCH, PK_PRE_LN, PK_LN, PK_GEMM_QKV, PK_ATTENTION, PK_GEMM_OUT, PK_GEMM_FC1,
-    PK_GEMM_FC2, PK_POOL, PK_SCORES, PK_SELECT, PK_GATHER, PK_RESIZE, PK_COUNT
+    PK_GEMM_FC2, PK_POOL, PK_SCORES, PK_SELECT, PK_GATHER, PK_RESIZE, PK_PROJECTION, PK_COUNT
 };
 struct ProfRec {
     int kind;
@@ -74,6 +74,10 @@ struct SasvqaEncoder {
     float *pos = nullptr, *cls_pos0 = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr;
     Layer L[kLayers];
     CUtensorMap m_patch_w;
+    // optional visual projection of the downstream GIT model (Linear 768->768 + LayerNorm): row f2
+    __nv_bfloat16* w_proj = nullptr;
+    float* proj_vec = nullptr;        // bias | ln gamma | ln beta
+    CUtensorMap m_proj;
     // workspace for one chunk
     float* x = nullptr;               // [chunk*197, 768]  fp32 residual stream
     __nv_bfloat16* h = nullptr;       // [chunk*197, 768]  LN output / attention output
@@ -380,6 +384,7 @@ void encoder_destroy(SasvqaEncoder* e) {
     if (!e) return;
     cudaFree(e->arena_bf16); cudaFree(e->arena_f32);
     cudaFree(e->x); cudaFree(e->h); cudaFree(e->big);
+    cudaFree(e->w_proj); cudaFree(e->proj_vec);
     cudaFree(e->feats); cudaFree(e->lcl);
     cudaFree(e->resized); cudaFree(e->picked); cudaFree(e->pick_map);
     for (int i = 0; i < 2; ++i) {
@@ -450,6 +455,86 @@ static int encode_frames(SasvqaEncoder* e, const uint8_t* u8, const float* f32, 
         {
             Scope sc(e, PK_POOL, s);
             if ((rc = launch_pool_norm(e->x, n, e->post_g, e->post_b, feats + (size_t)f0 * kHidden, s))) return rc;
+        }
+    }
+    return 0;
+}
+
+// ---- row f2: the visual side of the downstream video-QA forward on the sampled frames -------------------
+// src/modeling/modeling.py:76-95 (MyGitModel.forward): per frame `image_encoder(frame).last_hidden_state`
+// (ALL 197 tokens after post_layernorm), concatenated along the sequence, then `visual_projection`
+// (HF GitProjection: Linear(768, 768) + LayerNorm, eps 1e-5).  The image encoder IS the sampler's encoder, so
+// the K sampled frames of every clip run through the same kernels in one batch instead of a Python loop.
+int encoder_set_projection(SasvqaEncoder* e, const float* w_host, const float* b_host, const float* g_host,
+                           const float* beta_host) {
+    SASVQA_REQUIRE(e && w_host && b_host && g_host && beta_host, "null argument");
+    const size_t nw = (size_t)kHidden * kHidden;
+    float* raw = nullptr;
+    SASVQA_CUDA_CHECK(cudaMalloc(&raw, nw * sizeof(float)));
+    if (!e->w_proj && cudaMalloc(&e->w_proj, nw * sizeof(__nv_bfloat16)) != cudaSuccess) {
+        cudaFree(raw);
+        set_last_error("allocating projection weights failed");
+        return SASVQA_ERR_NOMEM;
+    }
+    if (!e->proj_vec && cudaMalloc(&e->proj_vec, 3 * kHidden * sizeof(float)) != cudaSuccess) {
+        cudaFree(raw);
+        set_last_error("allocating projection vectors failed");
+        return SASVQA_ERR_NOMEM;
+    }
+    cudaError_t ce = cudaMemcpy(raw, w_host, nw * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+        f32_to_bf16_kernel<<<592, 256>>>(raw, e->w_proj, (long long)nw);
+        ce = cudaMemcpy(e->proj_vec, b_host, kHidden * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->proj_vec + kHidden, g_host, kHidden * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(e->proj_vec + 2 * kHidden, beta_host, kHidden * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+    cudaFree(raw);
+    if (ce != cudaSuccess) {
+        set_last_error(std::string("uploading projection weights failed: ") + cudaGetErrorString(ce));
+        return SASVQA_ERR_CUDA;
+    }
+    return make_tensor_map_bf16_kmajor(&e->m_proj, e->w_proj, kHidden, kHidden, 128);
+}
+
+// frames (uint8 HWC 224x224 or normalised fp32 CHW -- the rows of the "sampled_frames" dataset) ->
+// tokens [n_frames * 197, 768] fp32: last_hidden_state (project == 0) or visual_projection(last_hidden_state)
+int visual_tokens(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int n_frames, int project, float* tokens,
+                  cudaStream_t s) {
+    SASVQA_REQUIRE(e != nullptr && n_frames >= 0, "bad arguments");
+    SASVQA_REQUIRE(n_frames == 0 || ((u8 != nullptr || f32 != nullptr) && tokens != nullptr), "null argument");
+    SASVQA_REQUIRE(!project || e->w_proj != nullptr, "no visual projection loaded (sasvqa_encoder_set_projection)");
+    for (int f0 = 0; f0 < n_frames; f0 += e->chunk_frames) {
+        const int n = std::min(e->chunk_frames, n_frames - f0);
+        const long long rows = (long long)n * kTokens;
+        float* out = tokens + (size_t)f0 * kTokens * kHidden;
+        int rc;
+        {
+            Scope sc(e, PK_PREPROCESS, s);
+            if (u8) rc = launch_preprocess_u8(u8 + (size_t)f0 * kFrameElems, n, e->big, s);
+            else rc = launch_patchify_f32(f32 + (size_t)f0 * kFrameElems, n, e->big, s);
+            if (rc) return rc;
+        }
+        if ((rc = encode_chunk(e, e->big, &e->m_big_patch, n, kLayers, s))) return rc;
+        if (!project) {                                          // post_layernorm of every token, fp32
+            Scope sc(e, PK_PROJECTION, s);
+            if ((rc = launch_layernorm_f32(e->x, out, rows, e->post_g, e->post_b, s))) return rc;
+            continue;
+        }
+        {
+            Scope sc(e, PK_LN, s);
+            if ((rc = launch_layernorm_bf16(e->x, e->h, (int)rows, e->post_g, e->post_b, s))) return rc;
+        }
+        {   // Linear: the residual-mode epilogue accumulates acc + bias into a zeroed fp32 buffer
+            Scope sc(e, PK_PROJECTION, s);
+            SASVQA_CUDA_CHECK(cudaMemsetAsync(e->x, 0, (size_t)rows * kHidden * sizeof(float), s));
+            GemmArgs g{};
+            g.A = e->h; g.B = e->w_proj; g.M = (int)rows; g.N = kHidden; g.K = kHidden;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = e->proj_vec; g.out_f32 = e->x;
+            if (e->use_simt) rc = launch_gemm_simt(g, s);
+            else rc = launch_gemm_tcgen05(g, &e->m_h, &e->m_proj, &e->m_out_x, e->num_sms, s);
+            if (rc) return rc;
+            if ((rc = launch_layernorm_f32(e->x, out, rows, e->proj_vec + kHidden, e->proj_vec + 2 * kHidden, s))) return rc;
         }
     }
     return 0;

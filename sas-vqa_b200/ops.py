@@ -86,7 +86,8 @@ class FrameEncoder:
 
     # ---- instrumentation
     PROFILE_KINDS = ("preprocess", "gemm_patch_embed", "pre_layernorm", "layernorm", "gemm_qkv", "attention",
-                     "gemm_out_proj", "gemm_fc1", "gemm_fc2", "pool_norm", "scores", "select", "gather", "resize")
+                     "gemm_out_proj", "gemm_fc1", "gemm_fc2", "pool_norm", "scores", "select", "gather", "resize",
+                     "projection")
 
     def profile_enable(self, on: bool = True) -> None:
         _capi.check(_capi.lib().sasvqa_profile_enable(self.handle, int(on)), "sasvqa_profile_enable")
@@ -98,6 +99,40 @@ class FrameEncoder:
         cnt = (ctypes.c_int64 * n)()
         _capi.check(_capi.lib().sasvqa_profile_read(self.handle, ms, cnt, n), "sasvqa_profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_KINDS)}
+
+    # ---- row f2: the downstream model's visual tokens on the sampled frames
+    def set_projection(self, weight: torch.Tensor, bias: torch.Tensor, ln_weight: torch.Tensor, ln_bias: torch.Tensor):
+        """Loads GIT's ``visual_projection`` (Linear(768, 768) + LayerNorm): ``visual_projection.0.weight``,
+        ``.0.bias``, ``.1.weight``, ``.1.bias`` of the reference's ``MyGitModel`` (src/modeling/modeling.py:93)."""
+        host = [t.detach().to("cpu", torch.float32).contiguous() for t in (weight, bias, ln_weight, ln_bias)]
+        if tuple(host[0].shape) != (HIDDEN, HIDDEN) or any(tuple(t.shape) != (HIDDEN,) for t in host[1:]):
+            raise ValueError("visual projection must be Linear(768, 768) + LayerNorm(768)")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib().sasvqa_encoder_set_projection(self.handle, *[t.data_ptr() for t in host]),
+                        "sasvqa_encoder_set_projection")
+
+    def visual_tokens(self, frames: torch.Tensor, project: bool = True) -> torch.Tensor:
+        """frames [..., 3, 224, 224] fp32 (processed frames, e.g. rows of ``sampled_frames``) or [..., 224, 224, 3]
+        uint8 on the GPU -> [..., 197, 768] fp32: ``image_encoder(frame).last_hidden_state`` per frame, passed
+        through ``visual_projection`` when ``project`` (src/modeling/modeling.py:76-95)."""
+        if not frames.is_cuda:
+            raise _capi.SasvqaError("frames must be a CUDA tensor (no CPU fallback)")
+        frames = frames.contiguous()
+        if frames.dtype == torch.float32 and tuple(frames.shape[-3:]) == (3, IMG, IMG):
+            fn, name = _capi.lib().sasvqa_visual_tokens_f32, "sasvqa_visual_tokens_f32"
+        elif frames.dtype == torch.uint8 and tuple(frames.shape[-3:]) == (IMG, IMG, 3):
+            fn, name = _capi.lib().sasvqa_visual_tokens_u8, "sasvqa_visual_tokens_u8"
+        else:
+            raise ValueError(f"frames must be fp32 [..., 3, 224, 224] or uint8 [..., 224, 224, 3], got "
+                             f"{frames.dtype} {tuple(frames.shape)}")
+        lead = tuple(frames.shape[:-3])
+        n = 1
+        for d in lead:
+            n *= d
+        out = torch.empty(lead + (TOKENS, HIDDEN), dtype=torch.float32, device=frames.device)
+        with torch.cuda.device(frames.device):
+            _capi.check(fn(self.handle, frames.data_ptr(), n, int(bool(project)), out.data_ptr(), _stream(frames)), name)
+        return out
 
     # ---- K2 + K3a
     def forward_patches(self, patches: torch.Tensor) -> torch.Tensor:

@@ -139,3 +139,16 @@ def sample_mif_batch(clips: torch.Tensor, model, question_embeds: torch.Tensor, 
     enc = as_frame_encoder(model)
     return ops.mif_sample_device(enc, clips, question_embeds.to(device=clips.device, dtype=torch.float32), K, ds_rate,
                                  want_frames=want_frames, want_aux=want_aux)
+
+
+def encode_sampled_frames(sampled: torch.Tensor, model, project: bool = True) -> torch.Tensor:
+    """The visual side of the downstream video-QA forward (src/modeling/modeling.py:76-95,
+    ``MyGitModel.forward`` with 5-D ``pixel_values``): ``sampled`` [B, K, 3, 224, 224] fp32 (what the collator
+    builds from the ``sampled_frames`` rows) -> [B, K * 197, 768]: per-frame ``last_hidden_state`` concatenated
+    along the sequence and passed through ``visual_projection`` (load it with ``FrameEncoder.set_projection``).
+    All K frames of all clips run as one batch through the sampler's encoder kernels."""
+    enc = as_frame_encoder(model)
+    if sampled.dim() != 5:
+        raise ValueError("pixel_values must be of rank 5: (batch_size, num_frames, num_channels, height, width)")
+    tok = enc.visual_tokens(sampled.to(enc.device), project=project)          # [B, K, 197, 768]
+    return tok.reshape(tok.shape[0], tok.shape[1] * tok.shape[2], tok.shape[3])

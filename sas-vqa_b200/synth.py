@@ -135,6 +135,22 @@ def random_encoder_state_dict(seed: int = REF_SEED, bf16_exact: bool = True) -> 
     return sd
 
 
+def random_projection_state_dict(seed: int = REF_SEED + 1, bf16_exact: bool = True) -> dict:
+    """Seeded weights of GIT's ``visual_projection`` (HF ``GitProjection``: Linear(768, 768) + LayerNorm) under its
+    own key names; the matrix is bf16-representable like the encoder matrices."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    w = 0.03 * torch.randn(HIDDEN, HIDDEN, generator=g)
+    if bf16_exact:
+        w = w.to(torch.bfloat16).to(torch.float32)
+    return {
+        "visual_projection.0.weight": w.contiguous(),
+        "visual_projection.0.bias": 0.02 * torch.randn(HIDDEN, generator=g),
+        "visual_projection.1.weight": 1.0 + 0.1 * torch.randn(HIDDEN, generator=g),
+        "visual_projection.1.bias": 0.02 * torch.randn(HIDDEN, generator=g),
+    }
+
+
 def question_embeddings(clip_ids, seed: int = REF_SEED, device="cpu") -> torch.Tensor:
     """Synthetic question text embeddings for the MIF workload (BASELINE config 3): one unit vector
     ``normalize(randn(768))`` per clip from ``Generator(seed + clip_id)`` -- the embedding-space surrogate of

@@ -455,3 +455,26 @@ def test_full_size_properties_c4_long_video(encoder):
         assert_same_or_tied(picks, want, lcl[b])
     one = sas.sample_mdf_batch(clips[1:2], encoder, K, W)
     assert torch.equal(one["indices"].cpu(), idx[1:2])
+
+
+# ------------------------------------------------------------------ row f2: visual tokens of the sampled frames
+def test_visual_tokens_vs_fp32_oracle_and_hf_fixture(encoder, vit_oracle, golden_dir):
+    """bf16 encoder + projection vs the fp32 chain of src/modeling/modeling.py:76-95.  Tolerance: the outputs are
+    LayerNorm-ed (unit scale); bf16 activations give |d| <= 0.06 per element, per-token cosine >= 0.9995."""
+    g = _golden(golden_dir, "visual_tokens_hf.npz")
+    psd = synth.random_projection_state_dict()
+    encoder.set_projection(*[psd[f"visual_projection.{k}"] for k in ("0.weight", "0.bias", "1.weight", "1.bias")])
+    clips = torch.stack([synth.make_clip(int(c), int(g["T"])) for c in g["clip_ids"]])          # [2, 2, 224, 224, 3] uint8
+    frames = torch.stack([vit.image_processor_224(c) for c in clips])                             # [2, 2, 3, 224, 224]
+    for project, probe in ((False, g["hidden_probe"]), (True, g["tokens_probe"])):
+        want = vit.visual_tokens(frames, vit_oracle, psd if project else None)
+        got = sas.encode_sampled_frames(frames.to(DEV), encoder, project=project).cpu()
+        assert got.shape == want.shape == (2, 2 * 197, 768)
+        cos = torch.nn.functional.cosine_similarity(got, want, dim=-1).min().item()
+        err = (got - want).abs().max().item()
+        assert cos >= 0.9995 and err <= 0.06, (project, cos, err)
+        assert np.abs(got[:, ::29, ::48].numpy() - probe).max() <= 0.06                         # HF's own output
+        got_u8 = encoder.visual_tokens(clips.to(DEV), project=project).reshape(2, 2 * 197, 768).cpu()
+        assert torch.equal(got_u8, got)                                                           # uint8 entry == fp32 entry
+    with pytest.raises(ValueError):
+        sas.encode_sampled_frames(frames[0].to(DEV), encoder)

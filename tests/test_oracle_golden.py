@@ -205,3 +205,18 @@ def test_resize_restatement_matches_torch_cpu_kernel_live():
         assert np.array_equal(resize.resize_crop_u8(img), ref[:, top:top + 224, left:left + 224]), (h, w)
     same = np.random.RandomState(1).randint(0, 256, (2, 224, 224, 3), dtype=np.uint8)
     assert np.array_equal(resize.resize_crop_u8(same), same)
+
+
+# ------------------------------------------------------------------ row f2 oracle: downstream visual tokens
+def test_visual_tokens_restatement_matches_hf_fixture(golden_dir):
+    """oracle.vit.visual_tokens == HF GitVisionModel + HF GitProjection as src/modeling/modeling.py:76-95 chains them."""
+    g = _load(golden_dir, "visual_tokens_hf.npz")
+    sd, psd = synth.random_encoder_state_dict(synth.REF_SEED), synth.random_projection_state_dict()
+    frames = torch.stack([vit.image_processor_224(synth.make_clip(int(c), int(g["T"]))) for c in g["clip_ids"]])
+    enc = vit.VitOracle(sd)
+    hidden = vit.visual_tokens(frames, enc, None)
+    tokens = vit.visual_tokens(frames, enc, psd)
+    assert tokens.shape == (2, 2 * 197, 768)
+    assert np.abs(hidden[:, ::29, ::48].numpy() - g["hidden_probe"]).max() <= 2e-4
+    assert np.abs(tokens[:, ::29, ::48].numpy() - g["tokens_probe"]).max() <= 2e-4
+    assert np.abs(tokens.double().sum(dim=-1).numpy() - g["tokens_rowsum"]).max() <= 2e-2
