@@ -2,9 +2,10 @@
 
 * ``sampled_frames``: float32 ``(N_videos, K, 3*IMG*IMG)`` rows, one per video in vidmapping
   order (reference writer: src/preprocessing/extract_features.py:77-79,96-97; reader:
-  src/datasets/dataset_base.py:104, src/datasets/dataset_video_qa.py:53-56).  Written as HDF5
-  through h5py when it is importable; this image has no h5py, so the same array is otherwise
-  written as ``<name>.npy`` (memory-mapped) and read back through ``open_sampled_frames``.
+  src/datasets/dataset_base.py:104, src/datasets/dataset_video_qa.py:53-56).  ``*.h5`` paths are
+  written as HDF5: through h5py when it is importable, else by the hand-laid-out writer in
+  ``hdf5_min.py`` (this image has no h5py / libhdf5); other paths get the same array as
+  ``<name>.npy`` (memory-mapped).  ``open_sampled_frames`` reads all three back.
 * ``vidmapping.json``: ``{video_id_without_ext: row}`` (extract_features.py:25-30).
 * ``qa_winds_{split}.json``: the QA list with ``sampled_inds`` added, best first
   (src/preprocessing/gen_sample.py:90-94; read at src/tasks/run_video_qa.py:72,91-92).
@@ -17,6 +18,8 @@ import json
 import os
 
 import numpy as np
+
+from . import hdf5_min
 
 try:  # pragma: no cover - h5py is absent in the build image
     import h5py  # type: ignore
@@ -40,13 +43,15 @@ class SampledFramesWriter:
 
     def __init__(self, path: str, n_videos: int, K: int, img: int = 224, backend: str | None = None):
         self.shape = (n_videos, K, 3 * img * img)
-        self.backend = backend or ("h5" if h5py is not None and path.endswith((".h5", ".hdf5")) else "npy")
-        if self.backend == "h5":
-            if h5py is None:
-                raise ImportError("h5py is not installed; use the .npy backend")
+        self.backend = backend or ("h5" if path.endswith((".h5", ".hdf5")) else "npy")
+        if self.backend == "h5" and h5py is not None:
             self.path = path
             self._fd = h5py.File(path, "w")
             self._ds = self._fd.create_dataset(DATASET, self.shape)          # float32, like the reference
+        elif self.backend == "h5":
+            self.path = path
+            self._fd = None
+            self._ds = hdf5_min.create_dataset_file(path, DATASET, self.shape, np.float32)
         else:
             self.path = path if path.endswith(".npy") else path + ".npy"
             self._fd = None
@@ -76,9 +81,9 @@ class SampledFramesWriter:
 def open_sampled_frames(path: str):
     """Row-indexable float32 array ``[N, K, 3*IMG*IMG]`` (what ``h5py.File(p,'r')['sampled_frames']`` gives)."""
     if path.endswith((".h5", ".hdf5")) and os.path.exists(path):
-        if h5py is None:
-            raise ImportError("h5py is not installed")
-        return h5py.File(path, "r")[DATASET]
+        if h5py is not None:
+            return h5py.File(path, "r")[DATASET]
+        return hdf5_min.open_datasets(path)[DATASET]
     return np.load(path if path.endswith(".npy") else path + ".npy", mmap_mode="r")
 
 
@@ -100,3 +105,20 @@ def write_mdf_inds(vidmapping: dict, indices, out_path: str) -> dict:
     with open(out_path, "w") as f:
         json.dump(rec, f)
     return rec
+
+
+def collate_sampled_rows(rows, samp_policy: str, nframe: int, sampled_inds=None, img: int = 224):
+    """Consumer-side view of the artefacts, restating the two sampling policies of the reference's collator that
+    read them (src/datasets/dataset_video_qa.py:356-361): ``rows`` [B, K, 3*img*img] (rows of ``sampled_frames``
+    looked up through vidmapping, dataset_video_qa.py:53-56) ->  [B, L, 3, img, img];
+    'importance' keeps the first ``nframe`` rows (MDF order = importance order), 'question-caption' takes rows
+    ``sampled_inds[:nframe]`` of each sample (the MIF indices of qa_winds_{split}.json)."""
+    rows = np.asarray(rows)
+    if samp_policy == "importance":
+        picked = rows[:, :nframe]
+    elif samp_policy == "question-caption":
+        inds = np.asarray([list(s[:nframe]) for s in sampled_inds], dtype=np.int64)
+        picked = rows[np.arange(rows.shape[0])[:, None], inds]
+    else:
+        raise ValueError("Sample strategy can only be chosen from ['importance', 'question-caption'] here")
+    return picked.reshape(picked.shape[0], picked.shape[1], 3, img, img)

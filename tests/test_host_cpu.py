@@ -125,6 +125,37 @@ def test_writers_round_trip(tmp_path):
     assert rec == {"vid12": [1, 2], "abc": [3, 4]}
 
 
+def test_hdf5_sampled_frames_round_trip_and_reader_pinned_on_genuine_file(tmp_path):
+    """The .h5 backend without h5py: hand-laid-out HDF5 (hdf5_min).  Its reader is first pinned on a file written
+    by libhdf5 itself (ships with scipy's test data: doubles linspace(0, 2*pi, 9)), then reads what we wrote."""
+    from sasvqa_b200 import hdf5_min
+    try:
+        import scipy.io.matlab
+        genuine = os.path.join(os.path.dirname(scipy.io.matlab.__file__), "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    except Exception:  # noqa: BLE001
+        genuine = ""
+    if os.path.exists(genuine):
+        ds = hdf5_min.open_datasets(genuine)
+        assert list(ds) == ["testdouble"] and ds["testdouble"].shape == (9, 1)
+        assert np.allclose(np.asarray(ds["testdouble"]).ravel(), np.linspace(0, 2 * np.pi, 9))
+    K, img = 4, 8
+    frames = torch.randn(3, K, 3, img, img)
+    path = str(tmp_path / "msvd_qa_video_feat.h5")
+    with writer.SampledFramesWriter(path, 3, K, img=img) as w:             # extract_features.py:77-79
+        for i in range(3):
+            w[i] = frames[i].reshape(K, -1)                                 # extract_features.py:96-97
+    raw = open(path, "rb").read(16)
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n"
+    ds = writer.open_sampled_frames(path)                                   # dataset_base.py:104
+    assert ds.shape == (3, K, 3 * img * img) and ds.dtype == np.float32
+    assert np.array_equal(np.asarray(ds), frames.reshape(3, K, -1).numpy())
+    # the two collator policies that consume these rows (dataset_video_qa.py:356-361)
+    imp = writer.collate_sampled_rows(ds[[0, 2]], "importance", 2, img=img)
+    assert np.array_equal(imp, frames[[0, 2], :2].numpy())
+    qc = writer.collate_sampled_rows(ds[[1, 2]], "question-caption", 3, [[3, 0, 2, 1], [1, 1, 0, 2]], img=img)
+    assert np.array_equal(qc[0], frames[1][[3, 0, 2]].numpy()) and np.array_equal(qc[1], frames[2][[1, 1, 0]].numpy())
+
+
 def test_shard_range_partitions():
     for n in (0, 1, 7, 256, 10000):
         for world in (1, 2, 3, 8):
