@@ -7,6 +7,7 @@ if the library is missing -- there is no CPU fallback.
 """
 from . import synth  # noqa: F401
 from ._capi import LIB_PATH, SasvqaError  # noqa: F401
+from .extract import generate_h5  # noqa: F401
 from .ops import FrameEncoder, STATUS_EMPTY, STATUS_FALLBACK, STATUS_OK, STATUS_TOO_FEW  # noqa: F401
 from .sampler import (  # noqa: F401
     encode_sampled_frames,
@@ -20,6 +21,6 @@ from .sampler import (  # noqa: F401
 )
 
 __all__ = [
-    "FrameEncoder", "SasvqaError", "encode_sampled_frames", "mif_select", "sample_frame_indices", "sample_frames_uniform",
+    "FrameEncoder", "SasvqaError", "encode_sampled_frames", "generate_h5", "mif_select", "sample_frame_indices", "sample_frames_uniform",
     "sample_mdf_batch", "sample_mdf_host", "sample_mif_batch", "sample_representative_frames", "synth",
 ]

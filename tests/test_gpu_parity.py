@@ -478,3 +478,37 @@ def test_visual_tokens_vs_fp32_oracle_and_hf_fixture(encoder, vit_oracle, golden
         assert torch.equal(got_u8, got)                                                           # uint8 entry == fp32 entry
     with pytest.raises(ValueError):
         sas.encode_sampled_frames(frames[0].to(DEV), encoder)
+
+
+# ------------------------------------------------------------------ extraction loop + on-disk artefacts
+def test_generate_h5_rows_match_reference_style_loop(encoder, tmp_path):
+    """generate_h5 (extract_features.py:41-111 over decoded clips) == one reference-signature sampler call per
+    clip, rows stored as extract_features.py:96-97 does; mixed frame sizes, an empty clip, all three strategies."""
+    from sasvqa_b200 import writer
+    K, W = 4, 2
+    clips = [synth.make_clip(80, 24), synth.make_clip(81, 24), synth.make_clip(82, 20, H=240, W=320),
+             torch.zeros(0, 224, 224, 3, dtype=torch.uint8), synth.make_clip(83, 24)]
+    path = str(tmp_path / "msvd_qa_video_feat.h5")
+    res = sas.generate_h5(clips, encoder, K, W, path, inds_outfile=str(tmp_path / "mdf_inds.json"))
+    ds = writer.open_sampled_frames(path)
+    assert ds.shape == (len(clips), K, 3 * 224 * 224) and res["debug_counter"]["Zeros"] == 1
+    from oracle import resize
+    dc = {"Failure": 0, "Zeros": 0}
+    for i, clip in enumerate(clips):
+        u8 = torch.from_numpy(resize.resize_crop_u8(clip.numpy())) if clip.shape[0] else clip
+        frames = vit.image_processor_224(u8) if clip.shape[0] else torch.zeros(0, 3, 224, 224)
+        want = sas.sample_representative_frames(frames, encoder, K, W, dc)          # the reference call, per clip
+        assert np.array_equal(np.asarray(ds[i]), want.reshape(K, -1).numpy()), i
+    assert dc == res["debug_counter"]
+    import json
+    assert json.load(open(tmp_path / "mdf_inds.json"))["1"] == res["indices"][1].tolist()
+    for strategy in ("uni", "git6"):
+        np.random.seed(666)
+        got = sas.generate_h5(clips[:2], None, K, W, str(tmp_path / f"{strategy}.h5"), sampling_strategy=strategy)
+        ds2 = writer.open_sampled_frames(str(tmp_path / f"{strategy}.h5"))
+        np.random.seed(666)
+        for i in range(2):
+            frames = vit.image_processor_224(clips[i])
+            want = sas.sample_frames_uniform(frames, K) if strategy == "uni" else \
+                sas.sample_frame_indices(frames, K, 4, len(frames))
+            assert np.array_equal(np.asarray(ds2[i]), want.reshape(K, -1).numpy()), (strategy, i)
