@@ -37,6 +37,14 @@ TOTAL_FLOP_PER_FRAME = GEMM_FLOP_PER_FRAME + 12 * (2 * 2 * 197 * 197 * 768)     
 # dram__bytes_read.sum + dram__bytes_write.sum of gemm_tcgen05_kernel from one `ncu --set full` capture at
 # chunk_frames=2048 (profiles/r01/ncu_gemm_v2_full.txt): qkv 2.43 GB, out_proj 3.04 GB, fc1 3.05 GB, fc2 5.16 GB
 # per launch -> mean over the four per-layer launches (the two patch-embed launches per step are negligible).
+# algorithmic bytes of the HBM-bound stages, per frame unless noted
+HBM_STAGE_BYTES_PER_FRAME = {
+    "preprocess": 150528 + 301056,                       # uint8 frame in, bf16 patch matrix out
+    "pre_layernorm": 2 * 197 * 768 * 4,                  # fp32 stream read + written in place
+    "layernorm": 24 * 197 * (768 * 4 + 768 * 2),         # 24 LayerNorms: fp32 row in, bf16 row out
+    "pool_norm": 197 * 768 * 4 + 768 * 4,                # fp32 hidden state in, one unit feature row out
+    "attention": 12 * 197 * (2304 * 2 + 768 * 2),        # q|k|v read once, heads written once (12 layers)
+}
 NCU_GEMM_DRAM_BYTES_PER_LAUNCH = {2048: (2.428e9 + 3.041e9 + 3.047e9 + 5.158e9) / 4}
 
 
@@ -276,6 +284,20 @@ def run_ours(args):
         "whole_path_frac_of_sustained": TOTAL_FLOP_PER_FRAME * B * T / (ms_per_step / 1e3) / 1e12 / peaks["tf_sustained"],
         "stage_ms_per_step": stage_ms,
     }
+
+    # achieved GB/s of the HBM-bound stages, from the same CUDA-event scopes
+    hbm = {}
+    for k, per_frame in HBM_STAGE_BYTES_PER_FRAME.items():
+        if prof.get(k, (0.0, 0))[0] > 0:
+            gbs = per_frame * frames_timed / (prof[k][0] / 1e3) / 1e9
+            hbm[k] = {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    per_clip = {"scores": T * 768 * 4 + T * 4, "gather": K * (150528 + 602112)}
+    for k, per in per_clip.items():
+        if prof.get(k, (0.0, 0))[0] > 0:
+            gbs = per * B * args.steps / (prof[k][0] / 1e3) / 1e9
+            hbm[k] = {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    roofline["hbm_stages"] = hbm
+    roofline["hbm_peak_gbs"] = peaks["hbm"]
 
     # ---- end to end through the host-buffer C-ABI call
     e2e = None

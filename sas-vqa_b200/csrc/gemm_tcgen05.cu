@@ -79,8 +79,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Arrive on a barrier of the peer CTA.  Plain arrive (release at CTA scope, what CUTLASS' ClusterBarrier::arrive
+// emits): the only thing the waiting MMA issuer needs ordered is this warp's TMEM reads, which
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync already give.  `.release.cluster` compiled to
+// MEMBAR.ALL.GPU + ERRBAR per warp per tile -- 30 % of the kernel's stall samples (profiles/r01/ncu_gemm_v4).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef SASVQA_HEAVY_ARRIVE
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
