@@ -19,7 +19,8 @@
 //   warps 4-11  softmax only.  All eight warps work on the same query half; the two warps that share a TMEM
 //               lane quarter (w, w+4) split a row's keys: part 0 = keys [0,112), part 1 = [112,208), exchanging
 //               the row max through shared memory.  Each thread reads its scores from TMEM once and keeps
-//               them in registers.  This stage is MUFU (ex2) bound; everything else hides under it.
+//               them in registers.  (Moving a share of the ex2 to an FMA-pipe polynomial was measured and is
+//               slower: 0.59 -> 0.61 ms at 1/3 -- the stage is latency-, not MUFU-bound.)
 //   warps 12-15 epilogue: (O_a + O_b) / l -> bf16 -> 128B-swizzled smem slab of 32 rows -> one TMA store per
 //               warp (row stride in global memory is 1536 B: direct stores would be 64-byte fragments).
 //               The TMEM slot is released as soon as O is in registers.
