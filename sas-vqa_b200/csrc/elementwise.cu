@@ -11,37 +11,45 @@ namespace {
 // Replaces the host image processor (reference: src/preprocessing/prefetch_loader.py:74-75) for
 // 224x224 input plus the im2col of the patch-embedding conv (HF modeling_git.py:461-467, :527).
 // Column order of a patch row = conv weight order: c*256 + iy*16 + ix.
-// One thread: 8 pixels x RGB = 24 contiguous input bytes -> three 16-byte bf16 stores.
+// The output is bf16, and for every one of the 3 x 256 possible inputs bf16(fma(u, 1/(255 std), -mean/std)) equals
+// bf16 of the processor's exact (u * (1/255) - mean) / std (checked exhaustively by the parity test), so the
+// streaming loop is loads, one FMA per value and stores.  One thread: the 16 pixels of one patch row = 48
+// contiguous input bytes (three 16-byte loads) -> for each channel 32 contiguous output bytes (two 16-byte stores).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ frames, int n_frames,
                                                              __nv_bfloat16* __restrict__ patches) {
-    const long long total = (long long)n_frames * kImg * (kImg / 8);
+    const float sc[3] = {(float)(1.0 / (255.0 * (double)0.26862954f)), (float)(1.0 / (255.0 * (double)0.26130258f)),
+                         (float)(1.0 / (255.0 * (double)0.27577711f))};
+    const float of[3] = {(float)(-(double)0.48145466f / (double)0.26862954f), (float)(-(double)0.4578275f / (double)0.26130258f),
+                         (float)(-(double)0.40821073f / (double)0.27577711f)};
+    const long long total = (long long)n_frames * kImg * kGrid;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int xc = (int)(i % (kImg / 8));
-        const long long fy = i / (kImg / 8);
+        const int px = (int)(i % kGrid);                         // patch column
+        const long long fy = i / kGrid;
         const int y = (int)(fy % kImg);
         const long long f = fy / kImg;
-        const uint2* src = reinterpret_cast<const uint2*>(frames + ((fy * kImg) + xc * 8) * 3);
-        uint2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-        uint32_t w[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
-        float v[3][8];
+        const uint4* src = reinterpret_cast<const uint4*>(frames + ((fy * kImg) + px * kPatch) * 3);
+        const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        const uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        uint32_t o[3][8];                                        // [channel][pixel pair] packed bf16x2
 #pragma unroll
-        for (int b = 0; b < 24; ++b) {
-            const uint32_t u = (w[b >> 2] >> ((b & 3) * 8)) & 0xffu;
-            v[b % 3][b / 3] = normalize_px(u, px_mean(b % 3), px_std(b % 3));
-        }
-        const long long prow = f * kPatches + (y / kPatch) * kGrid + (xc >> 1);
-        __nv_bfloat16* dst = patches + prow * kHidden + (y % kPatch) * kPatch + (xc & 1) * 8;
+        for (int p = 0; p < 16; p += 2) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            uint4 o;
-            o.x = pack_bf16x2(v[c][0], v[c][1]);
-            o.y = pack_bf16x2(v[c][2], v[c][3]);
-            o.z = pack_bf16x2(v[c][4], v[c][5]);
-            o.w = pack_bf16x2(v[c][6], v[c][7]);
-            *reinterpret_cast<uint4*>(dst + c * (kPatch * kPatch)) = o;
+            for (int c = 0; c < 3; ++c) {
+                const int b0 = 3 * p + c, b1 = 3 * (p + 1) + c;
+                const float u0 = (float)((w[b0 >> 2] >> ((b0 & 3) * 8)) & 0xffu), u1 = (float)((w[b1 >> 2] >> ((b1 & 3) * 8)) & 0xffu);
+                o[c][p >> 1] = pack_bf16x2(fmaf(u0, sc[c], of[c]), fmaf(u1, sc[c], of[c]));
+            }
         }
+        const long long prow = f * kPatches + (y / kPatch) * kGrid + px;
+        __nv_bfloat16* dst = patches + prow * kHidden + (y % kPatch) * kPatch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)                              // one full 32-byte sector per store (sm_100 256-bit st)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c * (kPatch * kPatch)),
+                         "r"(o[c][0]), "r"(o[c][1]), "r"(o[c][2]), "r"(o[c][3]), "r"(o[c][4]), "r"(o[c][5]), "r"(o[c][6]),
+                         "r"(o[c][7])
+                         : "memory");
     }
 }
 
@@ -228,34 +236,45 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) gather_u8_kernel(const uint8_t* __restrict__ clips,
                                                          const int32_t* __restrict__ idx, int B, int T, int K,
                                                          float* __restrict__ out) {
-    const long long total = (long long)B * K * kImg * (kImg / 8);
+    __shared__ float lut[3][256];                                // exact normalised value of every possible input
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+        const int c = i >> 8;
+        lut[c][i & 255] = normalize_px((uint32_t)(i & 255), px_mean(c), px_std(c));
+    }
+    __syncthreads();
+    const long long total = (long long)B * K * kImg * (kImg / 16);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int xc = (int)(i % (kImg / 8));
-        long long r = i / (kImg / 8);
+        const int xc = (int)(i % (kImg / 16));                   // 16 pixels = 48 input bytes per thread
+        long long r = i / (kImg / 16);
         const int y = (int)(r % kImg);
         const long long bk = r / kImg;
         const long long b = bk / K;
         const int t = idx[bk];
-        float v[3][8];
-        if (t >= 0 && t < T) {
-            const uint2* src = reinterpret_cast<const uint2*>(clips + (((b * T + t) * kImg + y) * kImg + xc * 8) * 3);
-            uint2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-            uint32_t w[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
-#pragma unroll
-            for (int q = 0; q < 24; ++q) {
-                const uint32_t u = (w[q >> 2] >> ((q & 3) * 8)) & 0xffu;
-                v[q % 3][q / 3] = normalize_px(u, px_mean(q % 3), px_std(q % 3));
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 24; ++q) v[q % 3][q / 3] = 0.f;
+        const bool ok = t >= 0 && t < T;
+        uint32_t w[12] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (ok) {
+            const uint4* src = reinterpret_cast<const uint4*>(clips + (((b * T + t) * kImg + y) * kImg + xc * 16) * 3);
+            const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+            w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
+            w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+            w[8] = w2.x; w[9] = w2.y; w[10] = w2.z; w[11] = w2.w;
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float4* dst = reinterpret_cast<float4*>(out + ((bk * 3 + c) * kImg + y) * kImg + xc * 8);
-            dst[0] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
-            dst[1] = make_float4(v[c][4], v[c][5], v[c][6], v[c][7]);
+            float v[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int q = 3 * p + c;
+                v[p] = ok ? lut[c][(w[q >> 2] >> ((q & 3) * 8)) & 0xffu] : 0.f;
+            }
+            float* dst = out + ((bk * 3 + c) * kImg + y) * kImg + xc * 16;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)                          // full 32-byte sectors (sm_100 256-bit stores)
+                asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * q), "f"(v[8 * q]),
+                             "f"(v[8 * q + 1]), "f"(v[8 * q + 2]), "f"(v[8 * q + 3]), "f"(v[8 * q + 4]), "f"(v[8 * q + 5]),
+                             "f"(v[8 * q + 6]), "f"(v[8 * q + 7])
+                             : "memory");
         }
     }
 }
@@ -284,8 +303,8 @@ inline int grid_for(long long work_items, int block, int cap = 148 * 16) {
 
 int launch_preprocess_u8(const uint8_t* frames_hwc, int n_frames, __nv_bfloat16* patches, cudaStream_t s) {
     if (n_frames == 0) return 0;
-    SASVQA_REQUIRE(((uintptr_t)frames_hwc & 7) == 0 && ((uintptr_t)patches & 15) == 0, "unaligned buffers");
-    const long long total = (long long)n_frames * kImg * (kImg / 8);
+    SASVQA_REQUIRE(((uintptr_t)frames_hwc & 15) == 0 && ((uintptr_t)patches & 31) == 0, "unaligned buffers");
+    const long long total = (long long)n_frames * kImg * kGrid;
     preprocess_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(frames_hwc, n_frames, patches);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -341,8 +360,8 @@ int launch_pool_norm(const float* x, int n_frames, const float* gamma, const flo
 
 int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s) {
     if (B == 0 || K == 0) return 0;
-    SASVQA_REQUIRE(((uintptr_t)clips & 7) == 0 && ((uintptr_t)out & 15) == 0, "unaligned buffers");
-    const long long total = (long long)B * K * kImg * (kImg / 8);
+    SASVQA_REQUIRE(((uintptr_t)clips & 15) == 0 && ((uintptr_t)out & 31) == 0, "unaligned buffers");
+    const long long total = (long long)B * K * kImg * (kImg / 16);
     gather_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(clips, idx, B, T, K, out);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();

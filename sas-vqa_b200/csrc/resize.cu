@@ -5,11 +5,11 @@
 // in oracle/resize.py).  224x224 input never comes here (resize and crop are identities).
 //
 // Frames [n, H, W, 3] uint8 -> [n, 224, 224, 3] uint8.  One CTA per (band of 16 output rows, frame):
-// the input rows the band needs are streamed once through a double-buffered shared-memory row segment
+// phase A streams the source rows the band needs once through a double-buffered shared-memory row segment
 // (16-byte coalesced loads of just the columns the crop needs); thread x makes the horizontal pass for its
-// output column (uint8 intermediate, as the reference does) and folds the row into the 16 x 3 int32
-// vertical accumulators it keeps in registers.  HBM-bound work: algorithmic bytes per frame =
-// H * (cropped source width) * 3 in + 150 528 out.
+// output column into a uint8 intermediate in shared memory (the reference also rounds to uint8 between the
+// passes); phase B makes the vertical pass over exactly the taps each output row has and the band leaves as
+// full 32-byte sectors.  Algorithmic bytes per frame = H * (cropped source width) * 3 in + 150 528 out.
 #include <math.h>
 
 #include <map>
@@ -24,7 +24,6 @@ namespace sasvqa {
 namespace {
 
 constexpr int OUT = kImg;            // 224
-constexpr int BAND = 16;             // output rows per CTA
 constexpr int MAX_TAPS = 64;         // filter taps per axis (source/224 up to ~15x)
 constexpr int RS_THREADS = 256;
 
@@ -100,6 +99,7 @@ struct DevicePlan {
     int H = 0, W = 0;
     int prec_x = 0, prec_y = 0, taps_x = 0, taps_y = 0;
     int x_lo = 0, seg_cols = 0;      // source columns [x_lo, x_lo + seg_cols) cover every horizontal tap
+    int band_rows[3] = {0, 0, 0};    // max source rows touched by a band of 16 / 8 / 4 output rows
     int32_t* xmin = nullptr;         // [224] relative to x_lo
     int32_t* xsize = nullptr;
     int16_t* wx = nullptr;           // [taps_x][224]
@@ -136,6 +136,12 @@ int get_plan(int H, int W, const DevicePlan** out) {
     int x_hi = 0;
     for (int o = 0; o < OUT; ++o) x_hi = std::max(x_hi, px.xmin[o] + px.xsize[o]);
     d.seg_cols = x_hi - d.x_lo;
+    const int bands[3] = {16, 8, 4};
+    for (int bi = 0; bi < 3; ++bi)
+        for (int r0 = 0; r0 < OUT; r0 += bands[bi]) {
+            const int last = r0 + bands[bi] - 1;
+            d.band_rows[bi] = std::max(d.band_rows[bi], py.xmin[last] + py.xsize[last] - py.xmin[r0]);
+        }
     std::vector<int32_t> xmin_rel(OUT);
     for (int o = 0; o < OUT; ++o) xmin_rel[o] = px.xmin[o] - d.x_lo;
     std::vector<int16_t> wy((size_t)OUT * py.taps, 0);           // row-major [224][taps_y]
@@ -175,26 +181,32 @@ __device__ __forceinline__ void load_segment(const uint8_t* __restrict__ src, lo
     }
 }
 
+// smem layout (bytes): [2 x seg_stride row segments][tmp: max_rows x 672 horizontal results][out: BAND x 672]
+//                      [wx: taps_x x 224 int16][wy: BAND x taps_y int16][ymin, ysize: BAND int32 each]
+template <int BAND>
 __global__ void __launch_bounds__(RS_THREADS)
 resize_crop_u8_kernel(const uint8_t* __restrict__ frames, long long total_bytes, int H, int W, int prec_x, int prec_y,
-                      int taps_x, int taps_y, int x_lo, int seg_cols, const int32_t* __restrict__ xmin,
+                      int taps_x, int taps_y, int x_lo, int seg_cols, int max_rows, const int32_t* __restrict__ xmin,
                       const int32_t* __restrict__ xsize, const int16_t* __restrict__ wx, const int32_t* __restrict__ ymin,
                       const int32_t* __restrict__ ysize, const int16_t* __restrict__ wy, const int32_t* __restrict__ frame_map,
                       long long src_frame0, int frame0, uint8_t* __restrict__ out) {
-    extern __shared__ __align__(16) uint8_t rs_smem[];
+    extern __shared__ __align__(32) uint8_t rs_smem[];
+    constexpr int ROW_BYTES = OUT * 3;                                             // 672
     const int seg_stride = ((seg_cols * 3 + 15 + 16) + 15) & ~15;                  // bytes per row-segment buffer
     uint8_t* seg0 = rs_smem;
-    int16_t* s_wx = reinterpret_cast<int16_t*>(rs_smem + 2 * seg_stride);          // [taps_x][224]
-    int16_t* s_wy = s_wx + taps_x * OUT;                                           // [BAND][taps_y]
+    uint8_t* tmp = rs_smem + 2 * seg_stride;
+    uint8_t* obuf = tmp + max_rows * ROW_BYTES;
+    int16_t* s_wx = reinterpret_cast<int16_t*>(obuf + BAND * ROW_BYTES);
+    int16_t* s_wy = s_wx + taps_x * OUT;
     int32_t* s_ymin = reinterpret_cast<int32_t*>(s_wy + BAND * taps_y + ((BAND * taps_y) & 1));
     int32_t* s_ysize = s_ymin + BAND;
 
     const int r0 = blockIdx.x * BAND, frame = frame0 + blockIdx.y;
     const int tid = threadIdx.x;
+    uint8_t* dst = out + ((size_t)frame * OUT + r0) * ROW_BYTES;                   // the band is contiguous in memory
     const long long src_frame = frame_map ? (long long)frame_map[frame] : src_frame0 + frame;   // < 0: zero rows
     if (src_frame < 0) {
-        uint8_t* o = out + ((size_t)frame * OUT + r0) * OUT * 3;
-        for (int i = tid; i < BAND * OUT * 3; i += RS_THREADS) o[i] = 0;
+        for (int i = tid; i < BAND * ROW_BYTES / 16; i += RS_THREADS) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     for (int i = tid; i < taps_x * OUT; i += RS_THREADS) s_wx[i] = wx[i];
@@ -209,23 +221,15 @@ resize_crop_u8_kernel(const uint8_t* __restrict__ frames, long long total_bytes,
     const long long frame_base = src_frame * H * W * 3;
     const int seg_bytes = seg_cols * 3;
 
-    int acc[BAND][3];
-#pragma unroll
-    for (int r = 0; r < BAND; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[r][c] = 1 << (prec_y - 1);
-
-    // prologue: first row segment
+    // ---- phase A: horizontal pass of every source row the band needs -> uint8 intermediate in shared memory
     long long g = frame_base + ((long long)y_lo * W + x_lo) * 3;
     load_segment(frames, g, seg_bytes, total_bytes, seg0);
     __syncthreads();
     for (int y = y_lo; y < y_hi; ++y) {
         const int buf = (y - y_lo) & 1;
         const uint8_t* seg = seg0 + buf * seg_stride + (int)(g & 15);
-        if (y + 1 < y_hi) {                                                        // prefetch the next row
-            const long long gn = g + (long long)W * 3;
-            load_segment(frames, gn, seg_bytes, total_bytes, seg0 + (buf ^ 1) * seg_stride);
-        }
+        if (y + 1 < y_hi)                                                          // prefetch the next row
+            load_segment(frames, g + (long long)W * 3, seg_bytes, total_bytes, seg0 + (buf ^ 1) * seg_stride);
         if (tid < OUT) {
             int h0 = 1 << (prec_x - 1), h1 = h0, h2 = h0;
             const uint8_t* p = seg + my_xmin * 3;
@@ -235,32 +239,60 @@ resize_crop_u8_kernel(const uint8_t* __restrict__ frames, long long total_bytes,
                 h1 += p[3 * j + 1] * w;
                 h2 += p[3 * j + 2] * w;
             }
-            h0 = clamp_u8(h0 >> prec_x);
-            h1 = clamp_u8(h1 >> prec_x);
-            h2 = clamp_u8(h2 >> prec_x);
-#pragma unroll
-            for (int r = 0; r < BAND; ++r) {
-                const int k = y - s_ymin[r];
-                if (k >= 0 && k < s_ysize[r]) {
-                    const int w = s_wy[r * taps_y + k];
-                    acc[r][0] += h0 * w;
-                    acc[r][1] += h1 * w;
-                    acc[r][2] += h2 * w;
-                }
-            }
+            uint8_t* t = tmp + (y - y_lo) * ROW_BYTES + tid * 3;
+            t[0] = (uint8_t)clamp_u8(h0 >> prec_x);
+            t[1] = (uint8_t)clamp_u8(h1 >> prec_x);
+            t[2] = (uint8_t)clamp_u8(h2 >> prec_x);
         }
         g += (long long)W * 3;
         __syncthreads();
     }
+    // ---- phase B: vertical pass, only the taps each output row really has
     if (tid < OUT) {
-        uint8_t* o = out + ((size_t)frame * OUT + r0) * OUT * 3 + tid * 3;
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < BAND; ++r) {
-            o[(size_t)r * OUT * 3 + 0] = (uint8_t)clamp_u8(acc[r][0] >> prec_y);
-            o[(size_t)r * OUT * 3 + 1] = (uint8_t)clamp_u8(acc[r][1] >> prec_y);
-            o[(size_t)r * OUT * 3 + 2] = (uint8_t)clamp_u8(acc[r][2] >> prec_y);
+            int v0 = 1 << (prec_y - 1), v1 = v0, v2 = v0;
+            const uint8_t* t = tmp + (s_ymin[r] - y_lo) * ROW_BYTES + tid * 3;
+            const int16_t* wr = s_wy + r * taps_y;
+            const int n = s_ysize[r];
+            for (int k = 0; k < n; ++k) {
+                const int w = wr[k];
+                v0 += t[k * ROW_BYTES] * w;
+                v1 += t[k * ROW_BYTES + 1] * w;
+                v2 += t[k * ROW_BYTES + 2] * w;
+            }
+            uint8_t* o = obuf + r * ROW_BYTES + tid * 3;
+            o[0] = (uint8_t)clamp_u8(v0 >> prec_y);
+            o[1] = (uint8_t)clamp_u8(v1 >> prec_y);
+            o[2] = (uint8_t)clamp_u8(v2 >> prec_y);
         }
     }
+    __syncthreads();
+    for (int i = tid; i < BAND * ROW_BYTES / 32; i += RS_THREADS) {               // full 32-byte sectors
+        const uint4 a = reinterpret_cast<const uint4*>(obuf)[2 * i], c = reinterpret_cast<const uint4*>(obuf)[2 * i + 1];
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * i), "r"(a.x), "r"(a.y),
+                     "r"(a.z), "r"(a.w), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w)
+                     : "memory");
+    }
+}
+
+template <int BAND>
+int launch_band(const DevicePlan* p, const uint8_t* frames, long long n_src, int H, int W, const int32_t* frame_map,
+                long long src_frame0, int n_frames, uint8_t* out, size_t smem, int max_rows, cudaStream_t s) {
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        SASVQA_CUDA_CHECK(cudaFuncSetAttribute(resize_crop_u8_kernel<BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    for (int f0 = 0; f0 < n_frames; f0 += 65535) {               // gridDim.y limit
+        const int n = std::min(65535, n_frames - f0);
+        resize_crop_u8_kernel<BAND><<<dim3(OUT / BAND, n), RS_THREADS, smem, s>>>(
+            frames, n_src * H * W * 3, H, W, p->prec_x, p->prec_y, p->taps_x, p->taps_y, p->x_lo, p->seg_cols, max_rows,
+            p->xmin, p->xsize, p->wx, p->ymin, p->ysize, p->wy, frame_map, src_frame0, f0, out);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+    }
+    return 0;
 }
 
 }  // namespace
@@ -290,23 +322,23 @@ int launch_resize_crop_u8(const uint8_t* frames, long long n_src, int H, int W, 
     const DevicePlan* p = nullptr;
     int rc = get_plan(H, W, &p);
     if (rc) return rc;
+    SASVQA_REQUIRE(((uintptr_t)out & 31) == 0, "output must be 32-byte aligned");
     const int seg_stride = ((p->seg_cols * 3 + 15 + 16) + 15) & ~15;
-    const size_t smem = 2 * (size_t)seg_stride + (size_t)p->taps_x * OUT * 2 + (size_t)(BAND * p->taps_y + 1) * 2 + 2 * BAND * 4 + 16;
-    SASVQA_REQUIRE(smem <= 200 * 1024, "frame too wide for the resize kernel's row buffer");
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        SASVQA_CUDA_CHECK(cudaFuncSetAttribute(resize_crop_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-    for (int f0 = 0; f0 < n_frames; f0 += 65535) {               // gridDim.y limit
-        const int n = std::min(65535, n_frames - f0);
-        resize_crop_u8_kernel<<<dim3(OUT / BAND, n), RS_THREADS, smem, s>>>(
-            frames, n_src * H * W * 3, H, W, p->prec_x, p->prec_y, p->taps_x, p->taps_y, p->x_lo, p->seg_cols, p->xmin,
-            p->xsize, p->wx, p->ymin, p->ysize, p->wy, frame_map, src_frame0, f0, out);
-        SASVQA_CUDA_CHECK(cudaGetLastError());
-        count_launch();
-    }
-    return 0;
+    // rows of source a band of `band` output rows can touch (ymin is monotonic with slope <= H / 224 + 1)
+    auto plan_smem = [&](int band, int* max_rows) {
+        *max_rows = p->band_rows[band == 16 ? 0 : (band == 8 ? 1 : 2)];
+        return 2 * (size_t)seg_stride + (size_t)(*max_rows) * OUT * 3 + (size_t)band * OUT * 3 + (size_t)p->taps_x * OUT * 2 +
+               (size_t)(band * p->taps_y + 1) * 2 + 2 * band * 4 + 32;
+    };
+    int max_rows = 0;
+    const size_t kLimit = 200 * 1024;
+    size_t smem = plan_smem(16, &max_rows);
+    if (smem <= kLimit) return launch_band<16>(p, frames, n_src, H, W, frame_map, src_frame0, n_frames, out, smem, max_rows, s);
+    smem = plan_smem(8, &max_rows);
+    if (smem <= kLimit) return launch_band<8>(p, frames, n_src, H, W, frame_map, src_frame0, n_frames, out, smem, max_rows, s);
+    smem = plan_smem(4, &max_rows);
+    SASVQA_REQUIRE(smem <= kLimit, "frame too large for the resize kernel's shared-memory band");
+    return launch_band<4>(p, frames, n_src, H, W, frame_map, src_frame0, n_frames, out, smem, max_rows, s);
 }
 
 }  // namespace sasvqa

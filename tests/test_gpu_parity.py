@@ -142,6 +142,12 @@ def test_preprocess_u8_bit_exact_vs_oracle():
     assert torch.equal(patches.view(torch.int16), ref.view(torch.int16))
     patches2 = ops.patchify_f32(want.to(DEV)).cpu()
     assert torch.equal(patches2.view(torch.int16), ref.view(torch.int16))
+    # exhaustive: every one of the 3 x 256 possible channel values (the kernel's one-FMA form must round to the
+    # same bf16 as the processor's multiply / subtract / divide)
+    allv = (torch.arange(224 * 224 * 3, dtype=torch.int64) // 3 % 256).to(torch.uint8).reshape(1, 224, 224, 3)
+    want = vit.image_processor_224(allv)
+    ref = want.reshape(1, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(196, 768).to(torch.bfloat16)
+    assert torch.equal(ops.preprocess_u8(allv.to(DEV)).cpu().view(torch.int16), ref.view(torch.int16))
 
 
 def test_gather_bit_exact_vs_oracle():
