@@ -301,16 +301,16 @@ __device__ __forceinline__ void epilogue_patch_chunk(const EpiParams& p, uint32_
     if (row >= p.M) return;
     const int frame = row / kPatches, patch = row - frame * kPatches;
     const float4* p4 = reinterpret_cast<const float4*>(p.pos + (size_t)(1 + patch) * p.N + col);
-    float4* x4 = reinterpret_cast<float4*>(p.out_f32 + ((size_t)frame * kTokens + 1 + patch) * p.N + col);
+    float* x = p.out_f32 + ((size_t)frame * kTokens + 1 + patch) * p.N + col;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float4 e = __ldg(p4 + q);
-        float4 o;
-        o.x = __uint_as_float(v[4 * q + 0]) + e.x;
-        o.y = __uint_as_float(v[4 * q + 1]) + e.y;
-        o.z = __uint_as_float(v[4 * q + 2]) + e.z;
-        o.w = __uint_as_float(v[4 * q + 3]) + e.w;
-        x4[q] = o;
+    for (int q = 0; q < 4; ++q) {                               // 256-bit stores: every store fills a whole 32-byte sector
+        const float4 e0 = __ldg(p4 + 2 * q), e1 = __ldg(p4 + 2 * q + 1);
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x + 8 * q),
+                     "f"(__uint_as_float(v[8 * q + 0]) + e0.x), "f"(__uint_as_float(v[8 * q + 1]) + e0.y),
+                     "f"(__uint_as_float(v[8 * q + 2]) + e0.z), "f"(__uint_as_float(v[8 * q + 3]) + e0.w),
+                     "f"(__uint_as_float(v[8 * q + 4]) + e1.x), "f"(__uint_as_float(v[8 * q + 5]) + e1.y),
+                     "f"(__uint_as_float(v[8 * q + 6]) + e1.z), "f"(__uint_as_float(v[8 * q + 7]) + e1.w)
+                     : "memory");
     }
 }
 
