@@ -65,12 +65,13 @@ def make_clip(clip_id: int, T: int, device="cpu", seed: int = REF_SEED, H: int =
     return out
 
 
-def make_clips(clip_ids, T: int, device="cpu", seed: int = REF_SEED, structured: bool = True) -> torch.Tensor:
+def make_clips(clip_ids, T: int, device="cpu", seed: int = REF_SEED, structured: bool = True, H: int = IMG,
+               W: int = IMG) -> torch.Tensor:
     """Batch of clips ``[B, T, H, W, 3]`` uint8."""
     ids = list(clip_ids)
-    out = torch.empty(len(ids), T, IMG, IMG, 3, dtype=torch.uint8, device=device)
+    out = torch.empty(len(ids), T, H, W, 3, dtype=torch.uint8, device=device)
     for b, cid in enumerate(ids):
-        out[b] = make_clip(cid, T, device=device, seed=seed, structured=structured)
+        out[b] = make_clip(cid, T, device=device, seed=seed, H=H, W=W, structured=structured)
     return out
 
 
