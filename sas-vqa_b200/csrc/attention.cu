@@ -199,11 +199,8 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames,
     if (n_frames == 0) return 0;
     SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
     constexpr int smem = 2 * KEYS_PAD * 128;   // 53 248 B: above the 48 KiB static limit
-    static bool attr_set = false;
-    if (!attr_set) {
-        SASVQA_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static SmemAttrCache smem_attr;
+    if (int rc = smem_attr.ensure(attention_kernel, smem)) return rc;
     attention_kernel<<<n_frames * kHeads, ATT_THREADS, smem, s>>>(qkv, out);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();

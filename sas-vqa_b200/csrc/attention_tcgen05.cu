@@ -533,12 +533,8 @@ int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv
                              __nv_bfloat16* out, int n_frames, int num_sms, cudaStream_t s, int variant) {
     if (n_frames == 0) return 0;
     SASVQA_REQUIRE(((uintptr_t)out & 15) == 0, "unaligned attention output");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SASVQA_CUDA_CHECK(
-            cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        attr_set = true;
-    }
+    static SmemAttrCache smem_attr;
+    if (int rc = smem_attr.ensure(attention_tcgen05_kernel, ATT_SMEM)) return rc;
     const int n_items = n_frames * kHeads;
     const int grid = n_items < num_sms ? n_items : num_sms;
     attention_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(*map_q, *map_kv, *map_out, out, n_items, variant);

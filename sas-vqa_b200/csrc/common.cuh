@@ -49,6 +49,22 @@ void count_launch(int n = 1);   // every kernel launch of this library is counte
         }                                                                                    \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember the largest size set on each one
+// (one process per GPU is the normal deployment, but nothing here may silently depend on it)
+struct SmemAttrCache {
+    size_t set[64] = {};
+    template <class Kernel>
+    int ensure(Kernel kernel, size_t bytes) {
+        int dev = 0;
+        SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || bytes > set[dev]) {
+            SASVQA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            if (dev >= 0 && dev < 64) set[dev] = bytes;
+        }
+        return 0;
+    }
+};
+
 // ---- epilogue modes of the encoder GEMM
 enum GemmEpilogue : int {
     EPI_BIAS_BF16 = 0,        // out_bf16 = acc + bias                         (fused q|k|v projection)

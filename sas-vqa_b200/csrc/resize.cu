@@ -279,11 +279,9 @@ resize_crop_u8_kernel(const uint8_t* __restrict__ frames, long long total_bytes,
 template <int BAND>
 int launch_band(const DevicePlan* p, const uint8_t* frames, long long n_src, int H, int W, const int32_t* frame_map,
                 long long src_frame0, int n_frames, uint8_t* out, size_t smem, int max_rows, cudaStream_t s) {
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        SASVQA_CUDA_CHECK(cudaFuncSetAttribute(resize_crop_u8_kernel<BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    static SmemAttrCache smem_attr;
+    if (smem > 48 * 1024)
+        if (int rc = smem_attr.ensure(resize_crop_u8_kernel<BAND>, smem)) return rc;
     for (int f0 = 0; f0 < n_frames; f0 += 65535) {               // gridDim.y limit
         const int n = std::min(65535, n_frames - f0);
         resize_crop_u8_kernel<BAND><<<dim3(OUT / BAND, n), RS_THREADS, smem, s>>>(
