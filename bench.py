@@ -313,7 +313,7 @@ def run_ours(args):
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tf_sustained"],
         "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sustained"],
         "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH.get(args.chunk_frames),
-        "traffic_note": "mean DRAM bytes per GEMM launch from ncu (profiles/r01/ncu_gemm_v4_full.txt); algorithmic "
+        "traffic_note": "mean DRAM bytes per GEMM launch from ncu (profiles/r01/ncu_gemm_v6_full.txt); algorithmic "
                         "operand+result bytes average 3.4e9 per launch at this chunk size",
         "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
         "flop_per_launch": GEMM_FLOP_PER_FRAME * frames_timed / max(gemm_launches, 1),

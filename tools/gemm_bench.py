@@ -16,7 +16,7 @@ for name, N, K, mode in shapes:
         ops.test_gemm(a, b, mode, vec, out_f32=x)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
+    reps = int(os.environ.get("REPS", "20"))
     e0.record()
     for _ in range(reps):
         ops.test_gemm(a, b, mode, vec, out_f32=x)
