@@ -8,14 +8,14 @@
 // (frame, head), queries in two halves h of 128 rows.  Roles:
 //   warp 0      TMA: Q (2 x 128 rows) + K (208 rows) and V (208 rows) -> 128B-swizzled smem; the Q|K and the V
 //               buffers are double buffered and recycled separately (Q|K die after S, V after P V)
-//   warp 1      MMA issuer: S_h = Q_h K^T  (M=128, N=208, K=64 -> 4 UMMAs, both operands K-major smem)
+//   warps 1-2   MMA issuers (one per half): S_h = Q_h K^T  (M=128, N=208, K=64 -> 4 UMMAs, both operands K-major smem)
 //                           O_h = P_h V    (M=128, N=64, K=208 -> 13 UMMAs; A = P from TMEM, B = V as an
 //                                           MN-major smem operand, i.e. V exactly as TMA delivered it).
 //               Back-to-back UMMAs into ONE accumulator are latency-chained (~150 cycles each at N=64,
 //               measured), so P V runs as two independent chains -- keys [0,112) -> O_a, keys [112,208) ->
 //               O_b, issued alternately -- and the epilogue adds the two accumulators.
-//               Issue order: PV_0(i), S_0(i+1), PV_1(i), S_1(i+1): the next item's scores are ready before
-//               the softmax warps finish the current item.
+//               Issue order per half h: PV_h(i), S_h(i+1): the next item's scores are ready before the softmax
+//               warps finish the current item.  Each half has its own issuing thread (warps 1 and 2).
 //   warps 4-11  softmax only.  All eight warps work on the same query half; the two warps that share a TMEM
 //               lane quarter (w, w+4) split a row's keys: part 0 = keys [0,112), part 1 = [112,208), exchanging
 //               the row max through shared memory.  Each thread reads its scores from TMEM once and keeps
@@ -196,6 +196,31 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {         
     return d;
 }
 
+// 2^x for x <= 0 on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], through the
+// round-to-nearest magic constant, a degree-3 polynomial for 2^f (max relative error 7.7e-5, far below the bf16
+// rounding of P) and an integer add of n into the exponent.  Every SASVQA_ATT_POLY_EVERY-th pair of scores takes
+// this path: the exponentials of one query half need 1792 MUFU cycles per SM sub-partition (16 ex2/clk/SM), which
+// bounds the softmax stage once the MMA chain is out of the way.
+#ifndef SASVQA_ATT_POLY_EVERY
+#define SASVQA_ATT_POLY_EVERY 0
+#endif
+__device__ __forceinline__ void exp2_poly_x2(float& p0, float& p1) {
+    const float kMagic = 12582912.0f;                            // 1.5 * 2^23
+    const uint64_t x = pack_f32x2(fmaxf(p0, -126.0f), fmaxf(p1, -126.0f));
+    const uint64_t t = add_f32x2(x, pack_f32x2(kMagic, kMagic));
+    const uint64_t n = add_f32x2(t, pack_f32x2(-kMagic, -kMagic));
+    const uint64_t f = fma_f32x2(n, pack_f32x2(-1.0f, -1.0f), x);
+    uint64_t r = fma_f32x2(f, pack_f32x2(0.05508868396282196f, 0.05508868396282196f),
+                           pack_f32x2(0.24260404706001282f, 0.24260404706001282f));
+    r = fma_f32x2(r, f, pack_f32x2(0.6932762265205383f, 0.6932762265205383f));
+    r = fma_f32x2(r, f, pack_f32x2(0.9999289512634277f, 0.9999289512634277f));
+    float t0, t1, r0, r1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(r, r0, r1);
+    p0 = __int_as_float(__float_as_int(r0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(r1) + (__float_as_int(t1) << 23));
+}
+
 // One thread's share of a softmax row: the NV = 112 (part 0, S columns [0,112)) or 96 (part 1, S columns
 // [112,208), of which 85 are real keys) scores are read from TMEM ONCE into registers; the row max is combined
 // with the partner warp through shared memory; P = exp2(S*scale - max) goes back as packed bf16 over the
@@ -234,8 +259,12 @@ __device__ __forceinline__ float softmax_part(uint32_t trow, Exchange&& exchange
         }
         float p0, p1;
         unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), scale2, neg_m2), p0, p1);
-        p0 = ex2(p0);
-        p1 = ex2(p1);
+        if (SASVQA_ATT_POLY_EVERY > 0 && j % SASVQA_ATT_POLY_EVERY == SASVQA_ATT_POLY_EVERY - 1) {
+            exp2_poly_x2(p0, p1);
+        } else {
+            p0 = ex2(p0);
+            p1 = ex2(p1);
+        }
         if (2 * j + 1 >= VALID) p1 = 0.f;
         acc[j & 1] = add_f32x2(acc[j & 1], pack_f32x2(p0, p1));
         pk[j] = pack_bf16x2(p0, p1);
@@ -304,9 +333,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     if (warp == 0 && lane == 0) {
         for (int b = 0; b < 2; ++b) {
             mbar_init(qk_full(b), 1);
-            mbar_init(qk_empty(b), 1);
+            mbar_init(qk_empty(b), 2);               // one commit per MMA issuer
             mbar_init(v_full(b), 1);
-            mbar_init(v_empty(b), 1);
+            mbar_init(v_empty(b), 2);
             mbar_init(s_full(b), 1);
             mbar_init(p_full(b), 256);
             mbar_init(o_full(b), 1);
@@ -347,9 +376,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                 mbar_arrive_expect_tx(v_full(b), KV_BYTES);
                 tma_load_2d(v_base + b * KV_BYTES, &map_kv, 2 * kHidden + head * kHeadDim, row, v_full(b));
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer =====================
-            auto issue_s = [&](uint32_t qk, int h) {           // S_h = Q_h K^T into slot h
+        } else if ((warp == 1 || warp == 2) && lane == 0) {
+            // ===================== MMA issuers: warp 1 drives query half 0, warp 2 half 1 =====================
+            // Two issuing threads so that neither half's chain  P_h ready -> P_h V -> slot free -> S_h(next)  waits
+            // behind the other half's barriers in program order (one thread cost ~650 cycles per item in such waits).
+            const int h = warp - 1;
+            auto issue_s = [&](uint32_t qk) {                  // S_h = Q_h K^T into slot h
                 const uint64_t adesc = desc_sw128(qk + h * Q_HALF_BYTES, 0);
                 const uint64_t bdesc = desc_sw128(qk + Q_BYTES, 0);
 #pragma unroll
@@ -358,7 +390,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                            k != 0);
                 tcgen05_commit(s_full(h));
             };
-            auto issue_pv = [&](uint32_t v_smem, int h) {      // O_h = P_h V, two alternating accumulator chains
+            auto issue_pv = [&](uint32_t v_smem) {             // O_h = P_h V, two alternating accumulator chains
                 const uint64_t vdesc = desc_sw128(v_smem, KEYS * 128);
                 const uint32_t slot = tmem_base + (uint32_t)(h * 256);
                 // 16 keys per UMMA = 8 packed-bf16 TMEM columns of P = 2048 B of V
@@ -375,38 +407,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             if ((int)blockIdx.x < n_items) {                    // prologue: scores of the first item
                 mbar_wait(qk_full(0), 0);
                 tcgen05_fence_after();
-                issue_s(smem_base, 0);
-                issue_s(smem_base, 1);
+                issue_s(smem_base);
                 tcgen05_commit(qk_empty(0));
             }
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int b = it & 1, nb = b ^ 1;
                 const uint32_t par = it & 1u;
                 const bool has_next = item + (int)gridDim.x < n_items;
-                const uint32_t qk_next = smem_base + nb * QK_BYTES;
                 mbar_wait(v_full(b), (it >> 1) & 1u);
-                mbar_wait(p_full(0), par);                      // softmax wrote P_0 into TMEM
+                mbar_wait(p_full(h), par);                      // softmax wrote P_h into TMEM
                 tcgen05_fence_after();
-                TR(0, 0);
-                issue_pv(v_base + b * KV_BYTES, 0);
+                TR(0, 2 * h);
+                issue_pv(v_base + b * KV_BYTES);
+                tcgen05_commit(v_empty(b));                     // (both issuers) V smem of this item reusable
                 if (has_next) {
                     mbar_wait(qk_full(nb), ((it + 1) >> 1) & 1u);
-                    mbar_wait(o_empty(0), par);                 // epilogue holds O_0 in registers: slot 0 reusable
+                    mbar_wait(o_empty(h), par);                 // epilogue holds O_h in registers: slot h reusable
                     tcgen05_fence_after();
-                    TR(0, 1);
-                    issue_s(qk_next, 0);
-                }
-                mbar_wait(p_full(1), par);
-                tcgen05_fence_after();
-                TR(0, 2);
-                issue_pv(v_base + b * KV_BYTES, 1);
-                tcgen05_commit(v_empty(b));                     // V smem of this item reusable
-                if (has_next) {
-                    mbar_wait(o_empty(1), par);
-                    tcgen05_fence_after();
-                    TR(0, 3);
-                    issue_s(qk_next, 1);
-                    tcgen05_commit(qk_empty(nb));               // Q|K smem of the next item reusable
+                    TR(0, 2 * h + 1);
+                    issue_s(smem_base + nb * QK_BYTES);
+                    tcgen05_commit(qk_empty(nb));               // (both issuers) Q|K smem of the next item reusable
                 }
             }
         }
