@@ -56,6 +56,9 @@ WORKLOADS = {
     "c3": dict(kind="mif", clips=256, frames=128, K=8, W=0, H=224, Wd=224,
                desc="MIF question-conditioned sampling, {clips} clips x {frames} frames per GPU with synthetic question "
                     "embeddings, K={K} (BASELINE configs[2])"),
+    "c3x": dict(kind="mif-captions", clips=256, frames=128, K=8, W=0, H=224, Wd=224,
+                desc="MIF with the reference's own relevance model: {clips} QA samples x {frames} captions per GPU scored by the "
+                     "BERT caption cross-encoder (gen_sample.py:79-88), strided top-K, K={K} (BASELINE configs[2], row f4)"),
     "c4": dict(kind="mdf", clips=64, frames=512, K=32, W=8, H=224, Wd=224,
                desc="MDF long-video sweep, {clips} clips x T={frames} frames per GPU, K={K}, W={W} (BASELINE configs[3])"),
     "c5": dict(kind="mdf+vqa", clips=1250, frames=64, K=16, W=4, H=240, Wd=320,
@@ -79,6 +82,7 @@ def parse():
     ap.add_argument("--W", type=int, default=None)
     ap.add_argument("--ds-rate", type=int, default=1, help="MIF stride (workload c3)")
     ap.add_argument("--chunk-frames", type=int, default=2048)
+    ap.add_argument("--max-tokens", type=int, default=131072, help="packed tokens per scorer pass (workload c3x)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -405,6 +409,165 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def run_mif_captions(args):
+    """Workload c3x: the MIF step with the reference's cross-encoder.  One step = G QA samples
+    x T captions tokenized once up front (the tokenizer is host Python in the reference too, gen_sample.py:80):
+    `value` = samples/s with the padded id matrices resident in HBM; `e2e` = the same through
+    sasvqa_mif_select_captions_host with the tokenizer's int64 host arrays in and the index table out."""
+    import torch
+    import torch.distributed as dist
+    import sasvqa_b200 as sas
+    from sasvqa_b200 import ops, sharding, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    G, T, K = args.clips, args.frames, args.K
+    sd = synth.random_scorer_state_dict()
+    scorer = sas.CaptionScorer(sd, max_tokens=args.max_tokens)
+    tok = synth.SynthTokenizer()
+    qa, caps = synth.make_qa_workload(G, T, seed=synth.REF_SEED + rank)
+    text, pair = [], []
+    for smp in qa:
+        text += [smp["question"]] * T
+        pair += caps[f"video{smp['video']}"]
+    batch = tok(text=text, text_pair=pair)
+    ids_h, tts_h, msk_h = batch["input_ids"], batch["token_type_ids"], batch["attention_mask"]
+    L = int(ids_h.shape[1])
+    n_tokens = int(msk_h.sum())
+    ids_d, tts_d = ids_h.to(dev, torch.int32), tts_h.to(dev, torch.int32)
+    n_total = G * world
+
+    def step():
+        logits = scorer.logits(ids_d, tts_d, msk_h)
+        idx = ops.topk_strided(logits[:, 0].contiguous().view(G, T), K, args.ds_rate)
+        table = sharding.all_gather_rows(idx, n_total) if world > 1 else idx
+        return logits, idx, table
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        logits, idx, table = step()
+    barrier()
+    launches0 = ops.launch_count()
+    scorer.profile(True)
+    sampler_thread = ClockSampler(physical_gpu_index(local_rank))
+    sampler_thread.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        logits, idx, table = step()
+    ev1.record()
+    barrier()
+    clocks = sampler_thread.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    prof = scorer.profile_read()
+    scorer.profile(False)
+    launches = ops.launch_count() - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n_total / (ms_per_step / 1e3)
+
+    gemm_flop_per_token = 12 * 2 * 768 * (2304 + 768 + 3072 + 3072)
+    gemm_ms = sum(v[0] for k, v in prof.items() if k.startswith("gemm_"))
+    gemm_launches = sum(v[1] for k, v in prof.items() if k.startswith("gemm_"))
+    achieved_tf = gemm_flop_per_token * n_tokens * args.steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    ln_bytes = 25 * n_tokens * (768 * 4 * 2 + 768 * 2)          # 25 LayerNorms: fp32 row in, fp32 + bf16 rows out
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tf_sustained"],
+        "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+        "peak_source": f"{peaks['src']} sustained bf16", "launches": gemm_launches,
+        "flop_per_launch": gemm_flop_per_token * n_tokens * args.steps / max(gemm_launches, 1),
+        "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+        "gemm_share_of_step": gemm_ms / max(sum(v[0] for v in prof.values()), 1e-9),
+        "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
+        "layernorm_gbs": ln_bytes * args.steps / max((prof["layernorm"][0] + prof["embed"][0]) / 1e3, 1e-9) / 1e9,
+        "hbm_peak_gbs": peaks["hbm"],
+    }
+
+    e2e = None
+    if not args.no_e2e:
+        idx_h = torch.empty(G, K, dtype=torch.int32, pin_memory=True)
+        pin = [x.pin_memory() for x in (ids_h, tts_h, msk_h)]
+
+        def e2e_step():
+            out, _ = scorer.select_captions_host(pin[0], pin[1], pin[2], G, K, args.ds_rate, idx_out=idx_h)
+            if world > 1:
+                sharding.all_gather_rows(out.to(dev), n_total)
+            return out
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out = e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_s = float(dt.item()) / args.e2e_steps
+        assert torch.equal(out, idx.cpu()), "host path and device path disagree"
+        e2e = {"value": n_total / e2e_s, "unit": "QA samples/s", "h2d_bytes_per_step": int(3 * ids_h.numel() * 8),
+               "d2h_bytes_per_step": int(idx_h.numel() * 4), "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
+               "api": "sasvqa_mif_select_captions_host (the tokenizer's int64 arrays in, [G, K] caption indices out)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import bert
+        torch.set_num_threads(os.cpu_count() or 1)
+        oracle_model = bert.BertScorerOracle(sd)
+        one = tok(text=text[:T], text_pair=pair[:T])                       # as the reference batches it: one QA sample
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            ref_logits = oracle_model(one["input_ids"], one["token_type_ids"], one["attention_mask"])
+            cpu_s = time.perf_counter() - t0
+        ref_idx = bert.mif_indices_from_logits(ref_logits, K, args.ds_rate)
+        gpu_idx = idx[0].cpu().tolist()
+        eps = (ref_logits[:, 0] - logits[:T, 0].cpu()).abs().max().item()
+        gap = max([abs(float(ref_logits[a, 0]) - float(ref_logits[b, 0])) for a, b in zip(gpu_idx, ref_idx) if a != b] or [0.0])
+        cpu = {"value": 1.0 / cpu_s, "unit": "QA samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"1 QA sample x {T} captions (the GPU arm's first sample), fp32 restatement of HF "
+                         "BertForSequenceClassification (oracle/bert.py) + the reference's top-K expression, 1 timed pass",
+               "cpu_indices": ref_idx, "gpu_indices": gpu_idx, "indices_identical": ref_idx == gpu_idx,
+               "max_abs_logit_error": eps, "max_score_gap_where_different": gap}
+
+    if rank == 0:
+        line = {
+            "metric": "MIF QA samples/sec through the caption cross-encoder", "value": value, "unit": "QA samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.desc.format(clips=G, frames=T, K=K, W=0) + ", random-init bert-base-cased classifier, "
+                                   "synthetic tokenizer", "samples_per_gpu": G, "captions_per_sample": T, "K": K,
+                       "padded_length": L, "tokens_per_step": n_tokens, "mean_tokens_per_pair": n_tokens / (G * T),
+                       "max_tokens_per_pass": scorer.max_tokens, "parallelism": f"dp{world} (QA samples sharded by rank)",
+                       "l2": f"{n_tokens * 10752 / 1e9:.2f} GB of activations per pass set, larger than L2"},
+            "captions_per_s": value * T, "tokens_per_s": n_tokens * world / (ms_per_step / 1e3), "clocks": clocks,
+            "gpu_launches": int(launches), "roofline": roofline,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        emit(line)
+    scorer.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def emit(line: dict) -> None:
     """The driver reads ONE JSON line from stdout: everything else (NCCL banners, library printf) was
     re-routed to stderr at start-up, the line goes to the saved real stdout."""
@@ -418,5 +581,7 @@ if __name__ == "__main__":
     os.dup2(2, 1)                 # C-level and Python-level stdout -> stderr from here on
     if a.impl == "reference":
         run_reference(a)
+    elif a.kind == "mif-captions":
+        run_mif_captions(a)
     else:
         run_ours(a)

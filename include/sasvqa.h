@@ -147,6 +147,49 @@ int sasvqa_visual_tokens_f32(SasvqaEncoder* enc, const float* frames_chw_dev, in
 int sasvqa_visual_tokens_u8(SasvqaEncoder* enc, const uint8_t* frames_hwc_dev, int n_frames, int project,
                             float* tokens_dev, void* stream);
 
+/* ---- MIF relevance model: caption cross-encoder (src/preprocessing/gen_sample.py:48-94) --------------------
+ * Replaces `AutoModelForSequenceClassification.from_pretrained(args.sim_model)` (gen_sample.py:160; a bert-base
+ * sequence classifier: 768 hidden, 12 layers x 12 heads, FFN 3072, 512 positions, 2 token types, LayerNorm eps
+ * 1e-12, erf GELU) and `output = model(**inputs); scores = output[0][:,0]` (gen_sample.py:82-83).
+ * params_host: the model's state_dict flattened to fp32 in HF key order: bert.embeddings.{word,position,token_type}
+ * _embeddings.weight, embeddings.LayerNorm.{weight,bias}, per layer attention.self.{query,key,value}.{weight,bias},
+ * attention.output.dense.{weight,bias}, attention.output.LayerNorm.{weight,bias}, intermediate.dense.{weight,bias},
+ * output.dense.{weight,bias}, output.LayerNorm.{weight,bias}, then bert.pooler.dense.{weight,bias},
+ * classifier.{weight,bias}.  n_params must equal sasvqa_scorer_num_params(vocab_size, num_labels).
+ * max_tokens: packed tokens per pass (workspace ~10.8 KB per token); <= 0 picks the default (65 536). */
+typedef struct SasvqaScorer SasvqaScorer;
+uint64_t sasvqa_scorer_num_params(int vocab_size, int num_labels);
+int sasvqa_scorer_create(const float* params_host, uint64_t n_params, int vocab_size, int num_labels, int max_tokens,
+                         SasvqaScorer** out);
+void sasvqa_scorer_destroy(SasvqaScorer* scorer);
+int sasvqa_scorer_max_tokens(const SasvqaScorer* scorer);
+/* Device entry: input_ids / token_type_ids [N, L] int32 as the tokenizer pads them (right padding; type ids may be
+ * NULL = all zero), lengths_host [N] = attention_mask.sum(1) (1 <= length <= L <= 512; positions past the length are
+ * never read) -> logits [N, num_labels] fp32.  Asynchronous on `stream`. */
+int sasvqa_scorer_logits(SasvqaScorer* scorer, const int32_t* input_ids_dev, const int32_t* token_type_ids_or_null_dev,
+                         const int32_t* lengths_host, int N, int L, float* logits_dev, void* stream);
+/* inspection: packed fp32 hidden state [sum(lengths), 768] after `n_layers` blocks (0 = embeddings); the call must
+ * fit one pass (sum(lengths) <= max_tokens) */
+int sasvqa_scorer_hidden(SasvqaScorer* scorer, const int32_t* input_ids_dev, const int32_t* token_type_ids_or_null_dev,
+                         const int32_t* lengths_host, int N, int L, int n_layers, float* hidden_dev, void* stream);
+/* Host entry: the tokenizer's int64 arrays as they are (`return_tensors='pt'`, gen_sample.py:80): input_ids,
+ * token_type_ids (or NULL), attention_mask (or NULL = no padding; must be ones then zeros) [N, L] -> logits in host
+ * memory.  Returns after the results are on the host. */
+int sasvqa_scorer_logits_host(SasvqaScorer* scorer, const int64_t* input_ids_host, const int64_t* token_type_ids_or_null_host,
+                              const int64_t* attention_mask_or_null_host, int N, int L, float* logits_host);
+/* Whole MIF step for G QA samples of T captions each (rows g*T .. g*T+T-1 of the [G*T, L] arrays are sample g's
+ * (question, caption_t) pairs): scores[g, t] = logits[g*T + t, label]; idx[g, :] = ds_rate * topk(scores[g, ::ds_rate], K),
+ * best first (gen_sample.py:83-88; label 0 there).  idx_host [G, K]; scores_or_null_host [G, T]. */
+int sasvqa_mif_select_captions_host(SasvqaScorer* scorer, const int64_t* input_ids_host,
+                                    const int64_t* token_type_ids_or_null_host, const int64_t* attention_mask_or_null_host,
+                                    int G, int T, int L, int K, int ds_rate, int label, int32_t* idx_host,
+                                    float* scores_or_null_host);
+/* per-stage timing of the scorer (same protocol as sasvqa_profile_*).  Kinds: 0 embed, 1 layernorm, 2 gemm_qkv,
+ * 3 attention, 4 gemm_out_proj, 5 gemm_fc1, 6 gemm_fc2, 7 pooler. */
+#define SASVQA_SCORER_PROFILE_KINDS 8
+int sasvqa_scorer_profile_enable(SasvqaScorer* scorer, int on);
+int sasvqa_scorer_profile_read(SasvqaScorer* scorer, double* ms_out, int64_t* scopes_out, int n_kinds);
+
 /* ---- instrumentation ------------------------------------------------------------------------
  * sasvqa_launch_count: kernels launched by this library in this process so far.
  * Profiling: when enabled, CUDA-event pairs bracket every stage launch on its stream;
@@ -161,7 +204,7 @@ int sasvqa_profile_read(SasvqaEncoder* enc, double* ms_out, int64_t* scopes_out,
 
 /* ---- test hooks (not on the product path) ---------------------------------------------------
  * One encoder GEMM with a fused epilogue (mode = 0 bias->bf16, 1 bias+quick_gelu->bf16,
- * 2 bias+residual in place fp32, 3 patch-embed scatter + position embedding).  use_simt != 0 runs
+ * 2 bias+residual in place fp32, 3 patch-embed scatter + position embedding, 4 bias+erf-gelu->bf16).  use_simt != 0 runs
  * the CUDA-core check kernel instead of the tcgen05 kernel. */
 int sasvqa_test_gemm(const uint16_t* a_bf16_dev, const uint16_t* b_bf16_dev, int M, int N, int K, int mode,
                      const float* bias_or_pos_dev, uint16_t* out_bf16_dev, float* out_f32_dev, int use_simt,
@@ -170,6 +213,9 @@ int sasvqa_test_gemm(const uint16_t* a_bf16_dev, const uint16_t* b_bf16_dev, int
 int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* out_bf16_dev, int impl, void* stream);
 int sasvqa_test_layernorm(const float* x_dev, int rows, const float* gamma_dev, const float* beta_dev,
                           uint16_t* out_bf16_dev, void* stream);
+/* variable-length attention of the scorer: packed qkv [M, 2304] bf16, cu_seqlens_dev [n_seqs + 1] -> out [M, 768] */
+int sasvqa_test_attention_varlen(const uint16_t* qkv_bf16_dev, const int32_t* cu_seqlens_dev, int n_seqs, int max_len,
+                                 uint16_t* out_bf16_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -227,9 +227,68 @@ def gen_resize():
     np.savez_compressed(os.path.join(GOLD, "resize_hf.npz"), **out)
 
 
+SCORER_VOCAB = 2048          # the vocabulary is only a gather table: a small one keeps weight generation fast
+
+
+def scorer_golden_inputs():
+    """Tokenized (question, caption) pairs the way gen_sample.py:80 builds them, plus edge rows: the shortest
+    possible pair, a single-text row, and a 512-token pair (truncation)."""
+    tok = synth.SynthTokenizer(SCORER_VOCAB)
+    qa, caps = synth.make_qa_workload(3, 6, seed=synth.REF_SEED)
+    text, pair = [], []
+    for s in qa:
+        text += [s["question"]] * 6
+        pair += caps[f"video{s['video']}"]
+    batch = tok(text=text, text_pair=pair, padding=True, truncation=True, return_tensors="pt")
+    long_q = " ".join(synth._WORDS[i % len(synth._WORDS)] for i in range(300))
+    long_c = " ".join(synth._WORDS[(7 * i) % len(synth._WORDS)] for i in range(400))
+    edge = tok(text=["", "what", long_q], text_pair=["", "a dog", long_c], padding=True, truncation=True, return_tensors="pt")
+    return qa, caps, batch, edge
+
+
+def gen_bert_scorer():
+    """HF BertForSequenceClassification (the class gen_sample.py:160 instantiates for a BERT checkpoint) with the
+    repo's seeded random bert-base weights -> logits of the golden inputs, and the reference's MIF expression
+    (gen_sample.py:83-88) evaluated on them."""
+    from transformers import BertConfig, BertForSequenceClassification
+    from oracle import bert
+    sd = synth.random_scorer_state_dict(vocab=SCORER_VOCAB)
+    model = BertForSequenceClassification(BertConfig(vocab_size=SCORER_VOCAB, num_labels=synth.BERT_LABELS)).eval()
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k or "token_type_ids" in k for k in missing), (missing, unexpected)
+    qa, caps, batch, edge = scorer_golden_inputs()
+    mine = bert.BertScorerOracle(sd)
+    out = {}
+    with torch.no_grad():
+        for name, b in (("batch", batch), ("edge", edge)):
+            ref = model(**b)[0]
+            got = mine(b["input_ids"], b["token_type_ids"], b["attention_mask"])
+            print(f"bert scorer {name}: shape {tuple(ref.shape)}, restatement max |d logit| = {(ref - got).abs().max():.2e}")
+            out[f"{name}_input_ids"] = b["input_ids"].numpy()
+            out[f"{name}_token_type_ids"] = b["token_type_ids"].numpy()
+            out[f"{name}_attention_mask"] = b["attention_mask"].numpy()
+            out[f"{name}_logits"] = ref.numpy()
+        hs = model.bert(**batch, output_hidden_states=True).hidden_states
+        out["batch_hidden0_row0"] = hs[0][0].numpy()              # embeddings output of the first pair
+        out["batch_hidden12_row0"] = hs[12][0].numpy()
+        # gen_sample.py:83-88 verbatim per QA sample (K = 3; ds_rate 1 and 2)
+        logits = torch.from_numpy(out["batch_logits"])
+        for ds_rate in (1, 2):
+            rows = []
+            for g in range(3):
+                scores = logits[g * 6:(g + 1) * 6][:, 0]
+                inds = scores[::ds_rate].topk(3)[1].detach().cpu().tolist()
+                rows.append([i * ds_rate for i in inds])
+            out[f"batch_inds_ds{ds_rate}"] = np.asarray(rows, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "bert_scorer_hf.npz"), vocab=np.int64(SCORER_VOCAB), **out)
+
+
 if __name__ == "__main__":
     if "--resize-only" in sys.argv:
         gen_resize()
+        sys.exit(0)
+    if "--scorer-only" in sys.argv:
+        gen_bert_scorer()
         sys.exit(0)
     if "--visual-only" in sys.argv:
         gen_visual_tokens()
@@ -242,3 +301,4 @@ if __name__ == "__main__":
     gen_encoder_and_e2e()
     gen_resize()
     gen_visual_tokens()
+    gen_bert_scorer()

@@ -40,6 +40,17 @@ SIGNATURES = {
     "sasvqa_mdf_sample_u8_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
     "sasvqa_mdf_sample_host": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_mdf_sample_host_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p]),
+    "sasvqa_scorer_num_params": (c_uint64, [c_int, c_int]),
+    "sasvqa_scorer_create": (c_int, [_p, c_uint64, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "sasvqa_scorer_destroy": (None, [_p]),
+    "sasvqa_scorer_max_tokens": (c_int, [_p]),
+    "sasvqa_scorer_logits": (c_int, [_p, _p, _p, _p, c_int, c_int, _p, _p]),
+    "sasvqa_scorer_hidden": (c_int, [_p, _p, _p, _p, c_int, c_int, c_int, _p, _p]),
+    "sasvqa_scorer_logits_host": (c_int, [_p, _p, _p, _p, c_int, c_int, _p]),
+    "sasvqa_mif_select_captions_host": (c_int, [_p, _p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p]),
+    "sasvqa_scorer_profile_enable": (c_int, [_p, c_int]),
+    "sasvqa_scorer_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
+    "sasvqa_test_attention_varlen": (c_int, [_p, _p, c_int, c_int, _p, _p]),
     "sasvqa_launch_count": (c_int64, []),
     "sasvqa_profile_enable": (c_int, [_p, c_int]),
     "sasvqa_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),

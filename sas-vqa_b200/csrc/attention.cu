@@ -49,7 +49,8 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r
 // one key chunk of NT*8 keys starting at key0: S = Q K^T, online softmax update, O += P V
 template <int NT>
 __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_t k_smem, uint32_t v_smem, int key0,
-                                             int lane, float (&m)[2], float (&l)[2], float (&o)[8][4]) {
+                                             int lane, float (&m)[2], float (&l)[2], float (&o)[8][4],
+                                             int n_valid = kTokens) {
     float s[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -72,7 +73,7 @@ __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_
         const int kcol = key0 + nt * 8 + 2 * (lane & 3);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const bool valid = (kcol + (e & 1)) < kTokens;
+            const bool valid = (kcol + (e & 1)) < n_valid;
             s[nt][e] = valid ? s[nt][e] * kScaleLog2 : -INFINITY;
             cmax[e >> 1] = fmaxf(cmax[e >> 1], s[nt][e]);
         }
@@ -193,7 +194,97 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     }
 }
 
+// ---- variable-length self-attention of the MIF cross-encoder (HF BertSelfAttention, modeling_bert.py:143-207,
+// reached from the reference at src/preprocessing/gen_sample.py:82).  Sequences are PACKED: rows
+// [cu[s], cu[s+1]) of qkv [M, 2304] belong to sequence s, so the tokenizer's padding never reaches the GPU and the
+// additive key mask of the reference (masked keys -> finfo.min before the softmax) reduces to "keys of my own
+// sequence".  One CTA of 4 warps per (sequence, head); K and V of the sequence are staged once (rows padded to a
+// multiple of 64 with zeros), each warp owns 16-query tiles and runs the same online-softmax chunk loop as above.
+constexpr int VAR_WARPS = 4;
+
+__global__ void __launch_bounds__(VAR_WARPS * 32)
+attention_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                        const int32_t* __restrict__ cu_seqlens, int row_base) {
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    const int head = blockIdx.x % kHeads;
+    const int seq = blockIdx.x / kHeads;
+    const long long row_begin = cu_seqlens[seq] - row_base;      // row_base = first packed row of this chunk
+    const int len = cu_seqlens[seq + 1] - cu_seqlens[seq];
+    if (len <= 0) return;
+    const int keys_pad = (len + 63) & ~63;
+    uint8_t* k_tile = att_smem;
+    uint8_t* v_tile = att_smem + keys_pad * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const __nv_bfloat16* base = qkv + row_begin * (long long)kQkv + head * kHeadDim;
+    const uint32_t k_smem = (uint32_t)__cvta_generic_to_shared(k_tile);
+    const uint32_t v_smem = (uint32_t)__cvta_generic_to_shared(v_tile);
+
+    for (int i = threadIdx.x; i < keys_pad * 8; i += VAR_WARPS * 32) {
+        const int r = i >> 3, c = i & 7;
+        if (r < len) {
+            const __nv_bfloat16* src = base + (long long)r * kQkv + c * 8;
+            cp_async16(k_smem + tile_off(r, c), src + kHidden);
+            cp_async16(v_smem + tile_off(r, c), src + 2 * kHidden);
+        } else {
+            *reinterpret_cast<uint4*>(k_tile + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(v_tile + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int q_tiles = (len + 15) >> 4;
+    for (int qt = warp; qt < q_tiles; qt += VAR_WARPS) {
+        const int row0 = qt * 16 + g, row1 = row0 + 8;
+        const int r0c = min(row0, len - 1), r1c = min(row1, len - 1);
+        uint32_t qf[4][4];
+        const __nv_bfloat16* q0 = base + (long long)r0c * kQkv + 2 * t;
+        const __nv_bfloat16* q1 = base + (long long)r1c * kQkv + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            qf[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 16 * ks));
+            qf[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 16 * ks));
+            qf[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 16 * ks + 8));
+            qf[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 16 * ks + 8));
+        }
+        float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, o[8][4];
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+        for (int key0 = 0; key0 < len; key0 += 64)          // every chunk starts below len: >= 1 valid key
+            attend_chunk<8>(qf, k_smem, v_smem, key0, lane, m, l, o, len);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+        }
+        const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+        __nv_bfloat16* o0 = out + (row_begin + row0) * (long long)kHidden + head * kHeadDim + 2 * t;
+        __nv_bfloat16* o1 = out + (row_begin + row1) * (long long)kHidden + head * kHeadDim + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            if (row0 < len) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+            if (row1 < len) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+        }
+    }
+}
+
 }  // namespace
+
+int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens_dev, int row_base,
+                            int n_seqs, int max_len, cudaStream_t s) {
+    if (n_seqs == 0) return 0;
+    SASVQA_REQUIRE(max_len >= 1 && max_len <= 512, "sequence length must be in [1, 512]");
+    SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
+    const int smem = 2 * ((max_len + 63) & ~63) * 128;      // <= 131 072 B
+    static SmemAttrCache smem_attr;
+    if (int rc = smem_attr.ensure(attention_varlen_kernel, smem)) return rc;
+    attention_varlen_kernel<<<n_seqs * kHeads, VAR_WARPS * 32, smem, s>>>(qkv, out, cu_seqlens_dev, row_base);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, cudaStream_t s) {
     if (n_frames == 0) return 0;

@@ -26,6 +26,17 @@ int visual_tokens(SasvqaEncoder*, const uint8_t*, const float*, int, int, float*
 int mif_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, const float*, int, int, int32_t*,
                       float*, float*, float*, cudaStream_t);
 
+uint64_t scorer_num_params(int, int);
+int scorer_create(const float*, uint64_t, int, int, int, SasvqaScorer**);
+void scorer_destroy(SasvqaScorer*);
+int scorer_max_tokens(const SasvqaScorer*);
+int scorer_logits(SasvqaScorer*, const int32_t*, const int32_t*, const int32_t*, int, int, float*, int, float*, cudaStream_t);
+int scorer_logits_host(SasvqaScorer*, const int64_t*, const int64_t*, const int64_t*, int, int, float*);
+int mif_select_captions_host(SasvqaScorer*, const int64_t*, const int64_t*, const int64_t*, int, int, int, int, int, int,
+                             int32_t*, float*);
+int scorer_profile_enable(SasvqaScorer*, int);
+int scorer_profile_read(SasvqaScorer*, double*, int64_t*, int);
+
 }  // namespace sasvqa
 
 using namespace sasvqa;
@@ -141,9 +152,46 @@ int sasvqa_mdf_sample_host_hw(SasvqaEncoder* enc, const uint8_t* clips_host, int
     return mdf_sample_host(enc, clips_host, B, T, H, Wd, K, W, idx_host, status_host, sampled_host);
 }
 
+uint64_t sasvqa_scorer_num_params(int vocab_size, int num_labels) {
+    return vocab_size >= 1 && num_labels >= 1 ? scorer_num_params(vocab_size, num_labels) : 0;
+}
+int sasvqa_scorer_create(const float* params_host, uint64_t n_params, int vocab_size, int num_labels, int max_tokens,
+                         SasvqaScorer** out) {
+    return scorer_create(params_host, n_params, vocab_size, num_labels, max_tokens, out);
+}
+void sasvqa_scorer_destroy(SasvqaScorer* scorer) { scorer_destroy(scorer); }
+int sasvqa_scorer_max_tokens(const SasvqaScorer* scorer) { return scorer_max_tokens(scorer); }
+int sasvqa_scorer_logits(SasvqaScorer* scorer, const int32_t* ids, const int32_t* type_ids, const int32_t* lengths_host, int N,
+                         int L, float* logits, void* stream) {
+    SASVQA_REQUIRE(N == 0 || logits != nullptr, "null logits");
+    return scorer_logits(scorer, ids, type_ids, lengths_host, N, L, logits, kLayers, nullptr, S(stream));
+}
+int sasvqa_scorer_hidden(SasvqaScorer* scorer, const int32_t* ids, const int32_t* type_ids, const int32_t* lengths_host, int N,
+                         int L, int n_layers, float* hidden, void* stream) {
+    SASVQA_REQUIRE(N == 0 || hidden != nullptr, "null hidden");
+    return scorer_logits(scorer, ids, type_ids, lengths_host, N, L, nullptr, n_layers, hidden, S(stream));
+}
+int sasvqa_scorer_logits_host(SasvqaScorer* scorer, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int N, int L,
+                              float* logits_host) {
+    return scorer_logits_host(scorer, ids, type_ids, mask, N, L, logits_host);
+}
+int sasvqa_mif_select_captions_host(SasvqaScorer* scorer, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int G,
+                                    int T, int L, int K, int ds_rate, int label, int32_t* idx_host, float* scores_host) {
+    return mif_select_captions_host(scorer, ids, type_ids, mask, G, T, L, K, ds_rate, label, idx_host, scores_host);
+}
+int sasvqa_scorer_profile_enable(SasvqaScorer* scorer, int on) { return scorer_profile_enable(scorer, on); }
+int sasvqa_scorer_profile_read(SasvqaScorer* scorer, double* ms, int64_t* scopes, int n_kinds) {
+    return scorer_profile_read(scorer, ms, scopes, n_kinds);
+}
+
+int sasvqa_test_attention_varlen(const uint16_t* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, uint16_t* out,
+                                 void* stream) {
+    SASVQA_REQUIRE(n_seqs == 0 || (qkv && cu_seqlens && out), "null argument");
+    return launch_attention_varlen(CBF(qkv), BF(out), cu_seqlens, 0, n_seqs, max_len, S(stream));
+}
 int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, int mode, const float* bias_or_pos,
                      uint16_t* out_bf16, float* out_f32, int use_simt, void* stream) {
-    SASVQA_REQUIRE(a && b && mode >= 0 && mode <= 3, "bad arguments");
+    SASVQA_REQUIRE(a && b && mode >= 0 && mode <= 4, "bad arguments");
     GemmArgs g{};
     g.A = CBF(a); g.B = CBF(b); g.M = M; g.N = N; g.K = K; g.epilogue = mode;
     g.bias = bias_or_pos; g.pos = bias_or_pos; g.out_bf16 = BF(out_bf16); g.out_f32 = out_f32;
@@ -153,7 +201,7 @@ int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, 
     if (rc) return rc;
     if ((rc = make_tensor_map_bf16_kmajor(&mb, b, (uint64_t)N, (uint64_t)K, 128))) return rc;
     CUtensorMap mo = ma;
-    if (mode == EPI_BIAS_BF16 || mode == EPI_BIAS_GELU_BF16) rc = make_tensor_map_out(&mo, out_bf16, (uint64_t)M, (uint64_t)N, 0);
+    if (mode == EPI_BIAS_BF16 || mode == EPI_BIAS_GELU_BF16 || mode == EPI_BIAS_ERF_GELU_BF16) rc = make_tensor_map_out(&mo, out_bf16, (uint64_t)M, (uint64_t)N, 0);
     else if (mode == EPI_BIAS_RESID_F32) rc = make_tensor_map_out(&mo, out_f32, (uint64_t)M, (uint64_t)N, 1);
     if (rc) return rc;
     int dev = 0, sms = 148;

@@ -71,6 +71,7 @@ enum GemmEpilogue : int {
     EPI_BIAS_GELU_BF16 = 1,   // out_bf16 = quick_gelu(acc + bias)             (fc1)
     EPI_BIAS_RESID_F32 = 2,   // x_f32   += acc + bias  (in place)             (out_proj, fc2)
     EPI_PATCH_EMBED_F32 = 3,  // x_f32[frame*197 + 1 + p] = acc + pos[1 + p]   (patch embedding)
+    EPI_BIAS_ERF_GELU_BF16 = 4,  // out_bf16 = gelu(acc + bias), exact erf form (BERT intermediate layer of the MIF scorer)
 };
 
 struct GemmArgs {
@@ -119,6 +120,19 @@ int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int
 int launch_gather_f32(const float* frames, const int32_t* idx, int B, int T, int K, int64_t row_elems, float* out,
                       cudaStream_t s);
 
+// MIF cross-encoder (BERT sequence classifier, src/preprocessing/gen_sample.py:79-83): packed variable-length rows
+int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens_dev, int row_base,
+                            int n_seqs, int max_len, cudaStream_t s);
+int launch_layernorm_post(float* x, __nv_bfloat16* h, long long rows, const float* gamma, const float* beta, float eps,
+                          cudaStream_t s);
+int launch_embed_layernorm(const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens, int row_base,
+                           int n_seqs, int L, int vocab, int n_types, const float* word, const float* pos,
+                           const float* type_emb, const float* gamma, const float* beta, float eps, float* x,
+                           __nv_bfloat16* h, cudaStream_t s);
+int launch_pooler_classifier(const float* x, const int32_t* cu_seqlens, int row_base, int n_seqs, const float* wp,
+                             const float* bp, const float* wc, const float* bc, int labels, float* logits,
+                             cudaStream_t s);
+
 // ---- device helpers
 #ifdef __CUDACC__
 
@@ -135,6 +149,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // x * sigmoid(1.702 x)  (HF "quick_gelu", modeling_git.py GitVisionMLP)
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+// 0.5 x (1 + erf(x / sqrt 2))  (HF "gelu", the BERT activation; modeling_bert.py BertIntermediate)
+__device__ __forceinline__ float erf_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // CLIPImageProcessor arithmetic for one channel value, rounded like torch on the CPU
 // (separate multiply, subtract, divide -- no FMA contraction): (u * (1/255) - mean) / std

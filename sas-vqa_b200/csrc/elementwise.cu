@@ -94,7 +94,7 @@ __device__ __forceinline__ void row_load(const float* __restrict__ row, int lane
 }
 
 __device__ __forceinline__ void row_normalize(RowRegs& r, int lane, const float* __restrict__ gamma,
-                                              const float* __restrict__ beta) {
+                                              const float* __restrict__ beta, float eps = kLnEps) {
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 6; ++j) s += (r.v[j].x + r.v[j].y) + (r.v[j].z + r.v[j].w);
@@ -108,7 +108,7 @@ __device__ __forceinline__ void row_normalize(RowRegs& r, int lane, const float*
         r.v[j].w -= mean;
         q += (r.v[j].x * r.v[j].x + r.v[j].y * r.v[j].y) + (r.v[j].z * r.v[j].z + r.v[j].w * r.v[j].w);
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kHidden) + kLnEps);
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kHidden) + eps);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -292,6 +292,132 @@ __global__ void __launch_bounds__(256) gather_f32_kernel(const float4* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// MIF cross-encoder (BERT, post-LN; eps 1e-12): the two elementwise stages around its GEMMs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row_store_both(const RowRegs& r, int lane, float* __restrict__ x,
+                                               __nv_bfloat16* __restrict__ h) {
+    float4* dx = reinterpret_cast<float4*>(x);
+    uint2* dh = reinterpret_cast<uint2*>(h);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        dx[lane + 32 * j] = r.v[j];
+        uint2 o;
+        o.x = pack_bf16x2(r.v[j].x, r.v[j].y);
+        o.y = pack_bf16x2(r.v[j].z, r.v[j].w);
+        dh[lane + 32 * j] = o;
+    }
+}
+
+// BertSelfOutput / BertOutput LayerNorm (modeling_bert.py:287-298, 345-356): the GEMM epilogue has already added
+// dense(.) + bias into the fp32 stream, so x <- LN(x) in place, and h <- bf16(x) is the next GEMM's A operand.
+__global__ void __launch_bounds__(256) layernorm_post_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ h,
+                                                              long long rows, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+         row += (long long)gridDim.x * warps_per_block) {
+        RowRegs r;
+        row_load(x + row * kHidden, lane, r);
+        row_normalize(r, lane, gamma, beta, eps);
+        row_store_both(r, lane, x + row * kHidden, h + row * kHidden);
+    }
+}
+
+// BertEmbeddings (modeling_bert.py:53-140): word[id] + position[p] + token_type[tt] -> LayerNorm, written to the
+// PACKED row cu[s] - row_base + p of x (fp32) and h (bf16).  One warp per (sequence, position) of the padded
+// [n_seqs, L] id matrix; positions at or past the sequence's length (the tokenizer's padding) are skipped.
+__global__ void __launch_bounds__(256)
+embed_layernorm_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ type_ids,
+                       const int32_t* __restrict__ cu_seqlens, int row_base, int n_seqs, int L, int vocab, int n_types,
+                       const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type_emb,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       float* __restrict__ x, __nv_bfloat16* __restrict__ h) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long total = (long long)n_seqs * L;
+    for (long long i = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < total;
+         i += (long long)gridDim.x * warps_per_block) {
+        const int s = (int)(i / L), p = (int)(i - (long long)s * L);
+        const int begin = cu_seqlens[s], len = cu_seqlens[s + 1] - begin;
+        if (p >= len) continue;
+        int id = ids[i], tt = type_ids ? type_ids[i] : 0;
+        id = min(max(id, 0), vocab - 1);                     // host side validates; never read out of the table
+        tt = min(max(tt, 0), n_types - 1);
+        RowRegs r, a, b;
+        row_load(word + (long long)id * kHidden, lane, r);
+        row_load(pos + (long long)p * kHidden, lane, a);
+        row_load(type_emb + (long long)tt * kHidden, lane, b);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {                        // (word + type) + position, the order HF adds them
+            r.v[j].x = (r.v[j].x + b.v[j].x) + a.v[j].x;
+            r.v[j].y = (r.v[j].y + b.v[j].y) + a.v[j].y;
+            r.v[j].z = (r.v[j].z + b.v[j].z) + a.v[j].z;
+            r.v[j].w = (r.v[j].w + b.v[j].w) + a.v[j].w;
+        }
+        row_normalize(r, lane, gamma, beta, eps);
+        const long long row = (long long)(begin - row_base) + p;
+        row_store_both(r, lane, x + row * kHidden, h + row * kHidden);
+    }
+}
+
+// BertPooler + classifier (modeling_bert.py:456-468, 1077-1155): logits[s] = Wc tanh(Wp x[cls(s)] + bp) + bc in
+// fp32.  One CTA per 8 sequences so that the 2.4 MB pooler matrix is streamed from L2 once per 8 rows: each warp
+// owns 96 of the 768 pooled outputs (lanes split the 768-long dot products, coalesced float4 weight loads), then
+// warp w computes the `labels` logits of sequence w.
+constexpr int POOL_SEQS = 8;
+__global__ void __launch_bounds__(256)
+pooler_classifier_kernel(const float* __restrict__ x, const int32_t* __restrict__ cu_seqlens, int row_base, int n_seqs,
+                         const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ wc,
+                         const float* __restrict__ bc, int labels, float* __restrict__ logits) {
+    __shared__ __align__(16) float cls[POOL_SEQS][kHidden];
+    __shared__ __align__(16) float pooled[POOL_SEQS][kHidden];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = blockIdx.x * POOL_SEQS;
+    for (int i = threadIdx.x; i < POOL_SEQS * (kHidden / 4); i += blockDim.x) {
+        const int q = i / (kHidden / 4), c = i - q * (kHidden / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s0 + q < n_seqs && cu_seqlens[s0 + q + 1] > cu_seqlens[s0 + q])
+            v = reinterpret_cast<const float4*>(x + (long long)(cu_seqlens[s0 + q] - row_base) * kHidden)[c];
+        reinterpret_cast<float4*>(cls[q])[c] = v;
+    }
+    __syncthreads();
+    for (int j = warp * (kHidden / 8); j < (warp + 1) * (kHidden / 8); ++j) {
+        const float4* w4 = reinterpret_cast<const float4*>(wp + (long long)j * kHidden);
+        float acc[POOL_SEQS];
+#pragma unroll
+        for (int q = 0; q < POOL_SEQS; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const float4 w = __ldg(w4 + lane + 32 * c);
+#pragma unroll
+            for (int q = 0; q < POOL_SEQS; ++q) {
+                const float4 v = reinterpret_cast<const float4*>(cls[q])[lane + 32 * c];
+                acc[q] = fmaf(w.x, v.x, fmaf(w.y, v.y, fmaf(w.z, v.z, fmaf(w.w, v.w, acc[q]))));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < POOL_SEQS; ++q) acc[q] = warp_sum(acc[q]);
+        if (lane < POOL_SEQS) {
+            float a = acc[0];
+#pragma unroll
+            for (int q = 1; q < POOL_SEQS; ++q) a = lane == q ? acc[q] : a;
+            pooled[lane][j] = tanhf(a + __ldg(bp + j));
+        }
+    }
+    __syncthreads();
+    const int s = s0 + warp;                                  // 8 warps <-> 8 sequences
+    if (s >= n_seqs) return;
+    for (int c = 0; c < labels; ++c) {
+        float a = 0.f;
+        for (int k = lane; k < kHidden; k += 32) a = fmaf(__ldg(wc + (long long)c * kHidden + k), pooled[warp][k], a);
+        a = warp_sum(a);
+        if (lane == 0) logits[(long long)s * labels + c] = a + __ldg(bc + c);
+    }
+}
+
 inline int grid_for(long long work_items, int block, int cap = 148 * 16) {
     long long g = (work_items + block - 1) / block;
     if (g > cap) g = cap;
@@ -376,6 +502,43 @@ int launch_gather_f32(const float* frames, const int32_t* idx, int B, int T, int
     const long long total = (long long)B * K * (row_elems / 4);
     gather_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(frames), idx, B, T, K,
                                                            row_elems / 4, reinterpret_cast<float4*>(out));
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace sasvqa
+
+namespace sasvqa {
+
+int launch_layernorm_post(float* x, __nv_bfloat16* h, long long rows, const float* gamma, const float* beta, float eps,
+                          cudaStream_t s) {
+    if (rows == 0) return 0;
+    layernorm_post_kernel<<<grid_for(rows, 8), 256, 0, s>>>(x, h, rows, gamma, beta, eps);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_embed_layernorm(const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens, int row_base,
+                           int n_seqs, int L, int vocab, int n_types, const float* word, const float* pos,
+                           const float* type_emb, const float* gamma, const float* beta, float eps, float* x,
+                           __nv_bfloat16* h, cudaStream_t s) {
+    if (n_seqs == 0 || L == 0) return 0;
+    embed_layernorm_kernel<<<grid_for((long long)n_seqs * L, 8), 256, 0, s>>>(ids, type_ids, cu_seqlens, row_base, n_seqs,
+                                                                              L, vocab, n_types, word, pos, type_emb,
+                                                                              gamma, beta, eps, x, h);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+int launch_pooler_classifier(const float* x, const int32_t* cu_seqlens, int row_base, int n_seqs, const float* wp,
+                             const float* bp, const float* wc, const float* bc, int labels, float* logits,
+                             cudaStream_t s) {
+    if (n_seqs == 0) return 0;
+    pooler_classifier_kernel<<<(n_seqs + POOL_SEQS - 1) / POOL_SEQS, 256, 0, s>>>(x, cu_seqlens, row_base, n_seqs, wp, bp,
+                                                                                   wc, bc, labels, logits);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -33,6 +33,9 @@ __global__ void gemm_simt_kernel(GemmArgs g) {
         case EPI_BIAS_GELU_BF16:
             g.out_bf16[(size_t)row * g.N + col] = __float2bfloat16_rn(quick_gelu(acc + g.bias[col]));
             break;
+        case EPI_BIAS_ERF_GELU_BF16:
+            g.out_bf16[(size_t)row * g.N + col] = __float2bfloat16_rn(erf_gelu(acc + g.bias[col]));
+            break;
         case EPI_BIAS_RESID_F32:
             g.out_f32[(size_t)row * g.N + col] += acc + g.bias[col];
             break;

@@ -242,6 +242,10 @@ __device__ __forceinline__ uint32_t epi_pair(uint32_t a0, uint32_t a1, float b0,
         asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(t1));
         const uint64_t hx = mul2(v, pk2(0.5f, 0.5f));
         upk2(fma2(hx, pk2(t0, t1), hx), f0, f1);
+    } else if (MODE == EPI_BIAS_ERF_GELU_BF16) {
+        upk2(v, f0, f1);
+        f0 = erf_gelu(f0);
+        f1 = erf_gelu(f1);
     } else {
         upk2(v, f0, f1);
     }
@@ -454,7 +458,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tcgen05_fence_after();
             const int row0 = m_blk * PAIR_M + (int)cta_rank * BLOCK_M + lane_grp * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BLOCK_N);
-            if (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
+            if (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_BIAS_ERF_GELU_BF16) {
 #pragma unroll 1
                 for (int c = col_lo; c < col_hi; c += 64, ++chunk_ctr)
                     epilogue_bf16_chunk<MODE>(epi, &map_out, taddr + (uint32_t)c,
@@ -559,6 +563,7 @@ int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUten
         case EPI_BIAS_GELU_BF16: return launch_mode<EPI_BIAS_GELU_BF16>(g, map_a, map_b, map_out, num_sms, stream);
         case EPI_BIAS_RESID_F32: return launch_mode<EPI_BIAS_RESID_F32>(g, map_a, map_b, map_out, num_sms, stream);
         case EPI_PATCH_EMBED_F32: return launch_mode<EPI_PATCH_EMBED_F32>(g, map_a, map_b, map_a, num_sms, stream);
+        case EPI_BIAS_ERF_GELU_BF16: return launch_mode<EPI_BIAS_ERF_GELU_BF16>(g, map_a, map_b, map_out, num_sms, stream);
         default: break;
     }
     SASVQA_REQUIRE(false, "unknown GEMM epilogue");

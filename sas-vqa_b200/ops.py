@@ -382,12 +382,12 @@ def test_gemm(a: torch.Tensor, b: torch.Tensor, mode: int, vec: torch.Tensor, ou
     b = _need_cuda(b, torch.bfloat16, "b")
     M, K = a.shape
     N = b.shape[0]
-    out_bf16 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if mode in (0, 1) else None
+    out_bf16 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if mode in (0, 1, 4) else None
     with torch.cuda.device(a.device):
         _capi.check(_capi.lib().sasvqa_test_gemm(a.data_ptr(), b.data_ptr(), M, N, K, mode, vec.data_ptr(),
                                                  _capi.ptr(out_bf16), _capi.ptr(out_f32), int(use_simt), _stream(a)),
                     "sasvqa_test_gemm")
-    return out_bf16 if mode in (0, 1) else out_f32
+    return out_bf16 if mode in (0, 1, 4) else out_f32
 
 
 def test_attention(qkv: torch.Tensor, impl: int = 0) -> torch.Tensor:

@@ -162,3 +162,135 @@ def question_embeddings(clip_ids, seed: int = REF_SEED, device="cpu") -> torch.T
         g.manual_seed(seed + int(cid))
         rows.append(torch.nn.functional.normalize(torch.randn(HIDDEN, generator=g), dim=0))
     return torch.stack(rows).to(device) if rows else torch.zeros(0, HIDDEN, device=device)
+
+
+# ---------------------------------------------------------------------------------------------
+# MIF relevance model (gen_sample.py:113,160: a bert-base-cased sequence classifier) -- synthetic
+# weights, tokenizer and (question, captions) workload; no checkpoint or vocabulary offline.
+# ---------------------------------------------------------------------------------------------
+BERT_VOCAB = 28996        # bert-base-cased
+BERT_MAX_POS = 512
+BERT_TYPES = 2
+BERT_LABELS = 2
+BERT_CLS, BERT_SEP, BERT_PAD = 101, 102, 0
+
+
+def scorer_state_dict_keys(vocab: int = BERT_VOCAB, labels: int = BERT_LABELS):
+    """HF ``BertForSequenceClassification.state_dict()`` key order (floating-point entries)."""
+    e = "bert.embeddings."
+    keys = [
+        (e + "word_embeddings.weight", (vocab, HIDDEN)),
+        (e + "position_embeddings.weight", (BERT_MAX_POS, HIDDEN)),
+        (e + "token_type_embeddings.weight", (BERT_TYPES, HIDDEN)),
+        (e + "LayerNorm.weight", (HIDDEN,)),
+        (e + "LayerNorm.bias", (HIDDEN,)),
+    ]
+    for l in range(LAYERS):
+        p = f"bert.encoder.layer.{l}."
+        for nm, shape in (("attention.self.query", (HIDDEN, HIDDEN)), ("attention.self.key", (HIDDEN, HIDDEN)),
+                          ("attention.self.value", (HIDDEN, HIDDEN)), ("attention.output.dense", (HIDDEN, HIDDEN))):
+            keys.append((p + nm + ".weight", shape))
+            keys.append((p + nm + ".bias", (shape[0],)))
+        keys.append((p + "attention.output.LayerNorm.weight", (HIDDEN,)))
+        keys.append((p + "attention.output.LayerNorm.bias", (HIDDEN,)))
+        keys.append((p + "intermediate.dense.weight", (FFN, HIDDEN)))
+        keys.append((p + "intermediate.dense.bias", (FFN,)))
+        keys.append((p + "output.dense.weight", (HIDDEN, FFN)))
+        keys.append((p + "output.dense.bias", (HIDDEN,)))
+        keys.append((p + "output.LayerNorm.weight", (HIDDEN,)))
+        keys.append((p + "output.LayerNorm.bias", (HIDDEN,)))
+    keys += [("bert.pooler.dense.weight", (HIDDEN, HIDDEN)), ("bert.pooler.dense.bias", (HIDDEN,)),
+             ("classifier.weight", (labels, HIDDEN)), ("classifier.bias", (labels,))]
+    return keys
+
+
+def random_scorer_state_dict(seed: int = REF_SEED + 2, vocab: int = BERT_VOCAB, labels: int = BERT_LABELS,
+                             bf16_exact: bool = True) -> dict:
+    """Seeded random bert-base sequence-classifier weights under HF key names (fp32, CPU).  Non-trivial LayerNorm
+    gains/biases and linear biases; the encoder-layer matrices (stored in bf16 on the GPU) are bf16-representable
+    with ``bf16_exact`` so the fp32 oracle and the kernels see identical weights."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sd = {}
+    for name, shape in scorer_state_dict_keys(vocab, labels):
+        if name.endswith("LayerNorm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif name.startswith("classifier") or "pooler" in name:
+            t = 0.05 * torch.randn(shape, generator=g)
+        elif "embeddings" in name:
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            t = 0.04 * torch.randn(shape, generator=g)
+            if bf16_exact:
+                t = t.to(torch.bfloat16).to(torch.float32)
+        sd[name] = t.contiguous()
+    return sd
+
+
+class SynthTokenizer:
+    """Stand-in for ``AutoTokenizer.from_pretrained(args.sim_model)`` (gen_sample.py:159) with the call signature
+    the reference uses (gen_sample.py:80): whitespace words hashed into the vocabulary, ``[CLS] a [SEP] b [SEP]``,
+    token types 0 / 1, right padding to the longest pair of the call, ``truncation`` to ``max_length`` by trimming
+    the longer side first (HF 'longest_first').  Returns int64 tensors like ``return_tensors='pt'``."""
+
+    def __init__(self, vocab: int = BERT_VOCAB, max_length: int = BERT_MAX_POS):
+        self.vocab, self.max_length = vocab, max_length
+
+    def _ids(self, text: str):
+        import zlib
+        lo = min(1000, self.vocab // 2)
+        return [lo + zlib.crc32(w.encode()) % (self.vocab - lo) for w in text.split()]
+
+    def __call__(self, text, text_pair=None, padding=True, truncation=True, return_tensors="pt", max_length=None):
+        max_length = max_length or self.max_length
+        rows = []
+        for i, a in enumerate(text):
+            ta = self._ids(a)
+            tb = self._ids(text_pair[i]) if text_pair is not None else None
+            if truncation:
+                budget = max_length - (3 if tb is not None else 2)
+                while len(ta) + (len(tb) if tb else 0) > budget:
+                    if tb and len(tb) >= len(ta):
+                        tb.pop()
+                    else:
+                        ta.pop()
+            ids = [BERT_CLS] + ta + [BERT_SEP]
+            types = [0] * len(ids)
+            if tb is not None:
+                ids += tb + [BERT_SEP]
+                types += [1] * (len(tb) + 1)
+            rows.append((ids, types))
+        L = max(len(r[0]) for r in rows) if rows else 0
+        input_ids = torch.full((len(rows), L), BERT_PAD, dtype=torch.long)
+        token_type_ids = torch.zeros(len(rows), L, dtype=torch.long)
+        attention_mask = torch.zeros(len(rows), L, dtype=torch.long)
+        for i, (ids, types) in enumerate(rows):
+            input_ids[i, :len(ids)] = torch.tensor(ids)
+            token_type_ids[i, :len(ids)] = torch.tensor(types)
+            attention_mask[i, :len(ids)] = 1
+        return {"input_ids": input_ids, "token_type_ids": token_type_ids, "attention_mask": attention_mask}
+
+
+_WORDS = ("a man woman dog cat child person is are playing cutting riding running cooking holding the guitar piano "
+          "horse bike ball food knife water street kitchen field room with on in near two people someone what who how "
+          "many does doing where red blue small large quickly slowly table car road grass").split()
+
+
+def make_qa_workload(n_samples: int, n_captions: int, seed: int = REF_SEED, min_words: int = 4, max_words: int = 14):
+    """Synthetic MSVD-QA-shaped annotations for the MIF step: ``(qa_samples, all_captions)`` --
+    ``qa_samples[i] = {'video': i, 'question': str, 'answer': str}`` and ``all_captions['video{i}']`` = one caption
+    per sampled frame (what gen_sample.py:20-45 writes to frame_captions.json)."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+
+    def sentence(lo, hi):
+        n = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        return " ".join(_WORDS[int(j)] for j in torch.randint(0, len(_WORDS), (n,), generator=g))
+
+    qa, caps = [], {}
+    for i in range(n_samples):
+        qa.append({"video": i, "question": sentence(4, 10) + " ?", "answer": _WORDS[i % len(_WORDS)]})
+        caps[f"video{i}"] = [sentence(min_words, max_words) for _ in range(n_captions)]
+    return qa, caps

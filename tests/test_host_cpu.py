@@ -197,3 +197,41 @@ def test_sharded_all_gather_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o
+
+
+def test_scorer_state_dict_flattening_and_hf_key_order():
+    from sasvqa_b200 import scorer
+    tr = pytest.importorskip("transformers")
+    vocab, labels = 64, 2
+    model = tr.BertForSequenceClassification(tr.BertConfig(vocab_size=vocab, num_labels=labels, num_hidden_layers=12))
+    hf = [(k, tuple(v.shape)) for k, v in model.state_dict().items() if v.is_floating_point()]
+    assert hf == [(k, tuple(s)) for k, s in synth.scorer_state_dict_keys(vocab, labels)]
+    flat, v, l = scorer.flatten_scorer_state_dict(model.state_dict())
+    assert (v, l) == (vocab, labels)
+    assert flat.numel() == _capi.lib().sasvqa_scorer_num_params(vocab, labels)      # host arithmetic only, no GPU
+    assert _capi.lib().sasvqa_scorer_num_params(28996, 2) == 108311810               # bert-base-cased, 2 labels
+    bad = dict(model.state_dict())
+    bad.pop("bert.pooler.dense.bias")
+    with pytest.raises(KeyError):
+        scorer.flatten_scorer_state_dict(bad)
+
+
+def test_synth_tokenizer_follows_the_bert_pair_layout():
+    tok = synth.SynthTokenizer(2048, max_length=16)
+    out = tok(text=["what is it ?", "who"], text_pair=["a dog", "a b c d e f g h i j k l m n o p q r"])
+    ids, tts, msk = out["input_ids"], out["token_type_ids"], out["attention_mask"]
+    assert ids.dtype == torch.int64 and ids.shape == (2, 16)
+    assert ids[0, :8].tolist()[0] == synth.BERT_CLS and ids[0, 5] == synth.BERT_SEP and ids[0, 8] == synth.BERT_SEP
+    assert tts[0].tolist() == [0] * 6 + [1] * 3 + [0] * 7 and msk[0].tolist() == [1] * 9 + [0] * 7
+    assert int(msk[1].sum()) == 16 and ids[1, 15] == synth.BERT_SEP          # truncated to max_length, SEP kept
+    assert ids[0, 9:].eq(synth.BERT_PAD).all()
+    single = tok(text=["a b"])
+    assert single["input_ids"].shape == (1, 4) and single["token_type_ids"].sum() == 0
+
+
+def test_scorer_needs_the_gpu_no_cpu_fallback():
+    from sasvqa_b200 import scorer
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(Exception):
+        scorer.CaptionScorer(synth.random_scorer_state_dict(vocab=32))

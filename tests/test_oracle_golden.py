@@ -220,3 +220,43 @@ def test_visual_tokens_restatement_matches_hf_fixture(golden_dir):
     assert np.abs(hidden[:, ::29, ::48].numpy() - g["hidden_probe"]).max() <= 2e-4
     assert np.abs(tokens[:, ::29, ::48].numpy() - g["tokens_probe"]).max() <= 2e-4
     assert np.abs(tokens.double().sum(dim=-1).numpy() - g["tokens_rowsum"]).max() <= 2e-2
+
+
+def test_bert_scorer_restatement_matches_hf_fixture(golden_dir):
+    """oracle/bert.py against HF BertForSequenceClassification's own outputs (tests/golden/bert_scorer_hf.npz,
+    written by oracle/make_golden.py with the seeded random bert-base weights), and the reference's MIF
+    expression (gen_sample.py:83-88) evaluated on HF's logits."""
+    from oracle import bert
+    import sasvqa_b200.synth as synth
+    g = _load(golden_dir, "bert_scorer_hf.npz")
+    sd = synth.random_scorer_state_dict(vocab=int(g["vocab"]))
+    model = bert.BertScorerOracle(sd)
+    for name in ("batch", "edge"):
+        ids, tts, msk = (torch.from_numpy(g[f"{name}_{k}"]) for k in ("input_ids", "token_type_ids", "attention_mask"))
+        logits = model(ids, tts, msk)
+        assert (logits - torch.from_numpy(g[f"{name}_logits"])).abs().max().item() <= 1e-4
+        if name == "batch":
+            h0 = model.hidden_states(ids, tts, msk, n_layers=0)[0]
+            h12 = model.hidden_states(ids, tts, msk)[0]
+            n = int(msk[0].sum())
+            assert (h0[:n] - torch.from_numpy(g["batch_hidden0_row0"])[:n]).abs().max().item() <= 1e-5
+            assert (h12[:n] - torch.from_numpy(g["batch_hidden12_row0"])[:n]).abs().max().item() <= 1e-4
+            for ds_rate in (1, 2):
+                for s in range(3):
+                    got = bert.mif_indices_from_logits(logits[s * 6:(s + 1) * 6], 3, ds_rate)
+                    assert got == g[f"batch_inds_ds{ds_rate}"][s].tolist()
+
+
+def test_bert_scorer_padding_is_invisible_in_the_oracle():
+    """The property the packed GPU path relies on: a pair's logits do not depend on how far it is padded."""
+    from oracle import bert
+    import sasvqa_b200.synth as synth
+    sd = synth.random_scorer_state_dict(vocab=512)
+    model = bert.BertScorerOracle(sd)
+    tok = synth.SynthTokenizer(512)
+    short = tok(text=["what is the man doing ?"], text_pair=["a man is cooking"])
+    padded = tok(text=["what is the man doing ?", "what is the man doing ?"],
+                 text_pair=["a man is cooking", "a woman is riding a horse near the water with two people"])
+    a = model(short["input_ids"], short["token_type_ids"], short["attention_mask"])
+    b = model(padded["input_ids"], padded["token_type_ids"], padded["attention_mask"])
+    assert (a[0] - b[0]).abs().max().item() <= 2e-5
