@@ -10,6 +10,8 @@
 // in shared memory with cp.async, 7 warps each own 16-query tiles (13 tiles) and run a
 // flash-style online softmax over key chunks 64/64/64/16 on bf16 mma.sync.m16n8k16 with fp32
 // accumulators.  (~4 % of the encoder's FLOPs; a tcgen05 version is listed in DESIGN.md "next".)
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sasvqa {
@@ -270,6 +272,83 @@ attention_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
     }
 }
 
+// Short sequences (max_len <= 64, the usual (question, caption) pair is ~20 tokens): a CTA per (sequence, head)
+// would leave three of its four warps idle and pay a block barrier per 20 tokens.  Here every WARP owns one
+// (sequence, head) item at a time: it stages that item's K and V in its private shared-memory slice (cp.async +
+// __syncwarp, no block barrier), and since all keys fit one chunk the softmax needs no online rescaling.
+// Consecutive warps take consecutive heads of one sequence, so their 128-byte row segments are neighbours in L2.
+__global__ void __launch_bounds__(VAR_WARPS * 32)
+attention_short_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                       const int32_t* __restrict__ cu_seqlens, int row_base, int n_items, int slice_bytes) {
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* k_tile = att_smem + warp * slice_bytes;
+    uint8_t* v_tile = k_tile + slice_bytes / 2;
+    const uint32_t k_smem = (uint32_t)__cvta_generic_to_shared(k_tile);
+    const uint32_t v_smem = (uint32_t)__cvta_generic_to_shared(v_tile);
+    const int g = lane >> 2, t = lane & 3;
+    for (int item = blockIdx.x * VAR_WARPS + warp; item < n_items; item += gridDim.x * VAR_WARPS) {
+        const int seq = item / kHeads, head = item - seq * kHeads;
+        const long long row_begin = cu_seqlens[seq] - row_base;
+        const int len = cu_seqlens[seq + 1] - cu_seqlens[seq];
+        if (len <= 0) continue;
+        const int keys_pad = (len + 15) & ~15;
+        const __nv_bfloat16* base = qkv + row_begin * (long long)kQkv + head * kHeadDim;
+        __syncwarp();                                          // previous item's ldmatrix reads are done
+        for (int i = lane; i < keys_pad * 8; i += 32) {
+            const int r = i >> 3, c = i & 7;
+            if (r < len) {
+                const __nv_bfloat16* src = base + (long long)r * kQkv + c * 8;
+                cp_async16(k_smem + tile_off(r, c), src + kHidden);
+                cp_async16(v_smem + tile_off(r, c), src + 2 * kHidden);
+            } else {
+                *reinterpret_cast<uint4*>(k_tile + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(v_tile + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const int q_tiles = keys_pad >> 4;
+        for (int qt = 0; qt < q_tiles; ++qt) {
+            const int row0 = qt * 16 + g, row1 = row0 + 8;
+            const int r0c = min(row0, len - 1), r1c = min(row1, len - 1);
+            uint32_t qf[4][4];
+            const __nv_bfloat16* q0 = base + (long long)r0c * kQkv + 2 * t;
+            const __nv_bfloat16* q1 = base + (long long)r1c * kQkv + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                qf[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 16 * ks));
+                qf[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 16 * ks));
+                qf[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 16 * ks + 8));
+                qf[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 16 * ks + 8));
+            }
+            float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, o[8][4];
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+            switch (q_tiles) {                                  // all keys in one chunk (16 keys per step)
+                case 1: attend_chunk<2>(qf, k_smem, v_smem, 0, lane, m, l, o, len); break;
+                case 2: attend_chunk<4>(qf, k_smem, v_smem, 0, lane, m, l, o, len); break;
+                case 3: attend_chunk<6>(qf, k_smem, v_smem, 0, lane, m, l, o, len); break;
+                default: attend_chunk<8>(qf, k_smem, v_smem, 0, lane, m, l, o, len); break;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+            }
+            const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+            __nv_bfloat16* o0 = out + (row_begin + row0) * (long long)kHidden + head * kHeadDim + 2 * t;
+            __nv_bfloat16* o1 = out + (row_begin + row1) * (long long)kHidden + head * kHeadDim + 2 * t;
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) {
+                if (row0 < len) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+                if (row1 < len) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens_dev, int row_base,
@@ -277,6 +356,18 @@ int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const 
     if (n_seqs == 0) return 0;
     SASVQA_REQUIRE(max_len >= 1 && max_len <= 512, "sequence length must be in [1, 512]");
     SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
+    if (max_len <= 64) {
+        const int slice = 2 * ((max_len + 15) & ~15) * 128;  // K + V of one item, <= 16 KiB per warp
+        const int smem = VAR_WARPS * slice;
+        static SmemAttrCache smem_short;
+        if (int rc = smem_short.ensure(attention_short_kernel, smem)) return rc;
+        const long long n_items = (long long)n_seqs * kHeads;
+        const int grid = (int)std::min<long long>((n_items + VAR_WARPS - 1) / VAR_WARPS, 148 * 16);
+        attention_short_kernel<<<grid, VAR_WARPS * 32, smem, s>>>(qkv, out, cu_seqlens_dev, row_base, (int)n_items, slice);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
     const int smem = 2 * ((max_len + 63) & ~63) * 128;      // <= 131 072 B
     static SmemAttrCache smem_attr;
     if (int rc = smem_attr.ensure(attention_varlen_kernel, smem)) return rc;

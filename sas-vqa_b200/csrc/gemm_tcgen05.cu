@@ -243,9 +243,25 @@ __device__ __forceinline__ uint32_t epi_pair(uint32_t a0, uint32_t a1, float b0,
         const uint64_t hx = mul2(v, pk2(0.5f, 0.5f));
         upk2(fma2(hx, pk2(t0, t1), hx), f0, f1);
     } else if (MODE == EPI_BIAS_ERF_GELU_BF16) {
+        // exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - |x / 2| erfc(|x| / sqrt 2), branch-free in packed
+        // fp32x2 math: erfc(t) = 2^(t q(t)) with a degree-7 fit of q on [0, 4] (|erf error| <= 1.3e-6 over all t >= 0,
+        // relative in erfc so the negative tail keeps its precision; libdevice erff in this epilogue cost fc1 25 %)
+        const uint64_t ax = v & 0x7fffffff7fffffffull;
+        const uint64_t t = mul2(ax, pk2(0.70710678f, 0.70710678f));            // no clamp: t q(t) keeps falling past 4
+        uint64_t q = fma2(pk2(-5.904118097532773e-06f, -5.904118097532773e-06f), t, pk2(6.987361120991409e-05f, 6.987361120991409e-05f));
+        q = fma2(q, t, pk2(-6.779028626624495e-05f, -6.779028626624495e-05f));
+        q = fma2(q, t, pk2(-0.003477875841781497f, -0.003477875841781497f));
+        q = fma2(q, t, pk2(0.030925802886486053f, 0.030925802886486053f));
+        q = fma2(q, t, pk2(-0.14975078403949738f, -0.14975078403949738f));
+        q = fma2(q, t, pk2(-0.9181910753250122f, -0.9181910753250122f));
+        q = fma2(q, t, pk2(-1.627914547920227f, -1.627914547920227f));
+        float e0, e1;
+        upk2(mul2(q, t), e0, e1);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(e0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(e1));
         upk2(v, f0, f1);
-        f0 = erf_gelu(f0);
-        f1 = erf_gelu(f1);
+        const uint64_t nh = mul2(ax, pk2(-0.5f, -0.5f));                       // -|x| / 2
+        upk2(fma2(nh, pk2(e0, e1), pk2(fmaxf(f0, 0.f), fmaxf(f1, 0.f))), f0, f1);
     } else {
         upk2(v, f0, f1);
     }

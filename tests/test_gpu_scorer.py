@@ -65,9 +65,21 @@ def test_gemm_erf_gelu_epilogue():
     for use_simt in (True, False):
         got = ops.test_gemm(a, b, 4, bias, use_simt=use_simt).float()
         assert (got - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    # the activation itself over its whole range, negative tail included: acc == x exactly (one non-zero product),
+    # so the output must be the bf16 rounding of fp32 gelu(x) to within one bf16 ulp
+    x = torch.cat([torch.linspace(-9.0, 9.0, 4001), torch.tensor([0.0, -0.0, 1e-6, -1e-6, 30.0, -30.0])])
+    x = x.to(torch.bfloat16)
+    a = torch.zeros(x.numel(), 64, dtype=torch.bfloat16)
+    a[:, 0] = x
+    b = torch.zeros(256, 64, dtype=torch.bfloat16)
+    b[:, 0] = 1.0
+    got = ops.test_gemm(a.to(DEV), b.to(DEV), 4, torch.zeros(256, device=DEV)).float().cpu()
+    want = torch.nn.functional.gelu(x.double()).float()
+    err = (got - want[:, None]).abs()
+    assert (err <= want.abs()[:, None] * 2.0 ** -8 + 1e-9).all(), float((err - want.abs()[:, None] * 2.0 ** -8).max())
 
 
-@pytest.mark.parametrize("lens", [[1], [2, 15, 16, 17], [64, 65, 63, 1, 128], [200, 3, 512, 77]], ids=str)
+@pytest.mark.parametrize("lens", [[1], [2, 15, 16, 17], [64, 33, 48, 1, 20, 49] * 40, [64, 65, 63, 1, 128], [200, 3, 512, 77]], ids=str)
 def test_attention_varlen_vs_fp32_reference(lens):
     torch.manual_seed(sum(lens))
     M = sum(lens)
