@@ -16,6 +16,13 @@ What it restates (reference = Clement25/SAS-VQA, read-only at /root/reference):
   and the HF ``CLIPImageProcessor`` arithmetic for 224x224 inputs
   (``src/preprocessing/prefetch_loader.py:74-75``).
 
+* ``oracle.bert`` -- the MIF relevance model the reference calls (``gen_sample.py:79-88,160``: HF
+  ``BertForSequenceClassification`` for a bert-base-cased checkpoint; math at
+  ``transformers/models/bert/modeling_bert.py``) and the ``generate_inds`` loop body around it; pinned
+  against HF itself with seeded random weights (``tests/golden/bert_scorer_hf.npz``).
+* ``oracle.resize`` -- the image processor's shortest-edge bicubic resize + centre crop
+  (``prefetch_loader.py:74-75`` -> HF ``CLIPImageProcessor`` -> ATen uint8 resampler).
+
 Pinning: the reference ships no tests or golden vectors.  ``oracle/make_golden.py`` imports
 the reference's own ``sample_representative_frames`` / ``sample_frames_uniform`` from
 /root/reference (and HF ``GitVisionModel`` / ``CLIPImageProcessor``) in the build container
