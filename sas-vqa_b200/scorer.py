@@ -218,7 +218,7 @@ def generate_inds(tokenizer, model, qa_samples: list, all_captions: dict, K: int
         vid_name, qid_temp = "video_id", "{}"
     else:
         raise ValueError("Invalid dataset name! Current supported dataset msvd_qa, msrvtt_qa")
-    if not isinstance(model, CaptionScorer):
+    if not hasattr(model, "select_captions_host"):          # an HF BertForSequenceClassification: upload it once
         model = CaptionScorer.from_model(model)
     new_ds = [None] * len(qa_samples)
     # group consecutive samples with equal caption counts (one H5 => one K for every video; be general anyway)

@@ -56,3 +56,27 @@ def sample_mdf_sharded(make_local_clips, n_clips: int, model, K: int, W: int, gr
         idx, status = idx.cuda(), status.cuda()
     return dict(indices=all_gather_rows(idx, n_clips, group), status=all_gather_rows(status, n_clips, group),
                 local=local, shard=(start, end))
+
+
+def generate_inds_sharded(tokenizer, model, qa_samples: list, all_captions: dict, K: int, ds_rate: int = 1,
+                          dataset: str = "msvd_qa", group=None, samples_per_call: int = 64) -> list:
+    """The MIF step (``gen_sample.py:50-92``) over one split with the QA list sharded by rank: QA samples are
+    independent, so each rank scores a contiguous slice with its own scorer replica and the ``[n, K]`` index table is
+    all-gathered -- every rank returns the complete ``qa_winds`` list (rank 0 writes it).  No data-path collective."""
+    from . import scorer as SC
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n = len(qa_samples)
+    start, end = shard_range(n, rank, world)
+    local = SC.generate_inds(tokenizer, model, qa_samples[start:end], all_captions, K, ds_rate, dataset=dataset,
+                             samples_per_call=samples_per_call)
+    idx = torch.tensor([r["sampled_inds"] for r in local], dtype=torch.int32).view(end - start, K)
+    if dist.is_initialized() and world > 1 and dist.get_backend(group) == "nccl":
+        idx = idx.cuda()
+    table = all_gather_rows(idx, n, group).cpu()
+    out = []
+    for i, sample in enumerate(qa_samples):
+        rec = dict(sample)
+        rec["sampled_inds"] = [int(v) for v in table[i]]
+        out.append(rec)
+    return out

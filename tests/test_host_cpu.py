@@ -183,6 +183,23 @@ want = torch.arange(n, dtype=torch.int32)[:, None] * 10 + torch.arange(K, dtype=
 assert torch.equal(res["indices"], want), res["indices"]
 assert torch.equal(res["status"], torch.arange(n, dtype=torch.int32) % 2)
 assert res["shard"] == sharding.shard_range(n, rank, world)
+# ---- MIF step sharded by QA sample: a stand-in scorer (deterministic scores from the token ids) on each rank
+from sasvqa_b200 import synth
+class FakeScorer:
+    def select_captions_host(self, ids, tts, msk, n_samples, K_, ds_rate=1, label=0, want_scores=False, idx_out=None):
+        T = ids.shape[0] // n_samples
+        scores = ((ids * msk).sum(1) % 97).float().view(n_samples, T)
+        idx = scores[:, ::ds_rate].topk(K_, dim=1)[1].to(torch.int32) * ds_rate
+        return idx, None
+tok = synth.SynthTokenizer(2048)
+qa, caps = synth.make_qa_workload(9, 6, seed=5)
+full = sharding.generate_inds_sharded(tok, FakeScorer(), qa, caps, 3, 2, samples_per_call=2)
+assert [r["question"] for r in full] == [r["question"] for r in qa] and len(full) == 9
+for smp, rec in zip(qa, full):
+    c = caps["video%d" % smp["video"]]
+    b = tok(text=[smp["question"]] * len(c), text_pair=c)
+    sc = ((b["input_ids"] * b["attention_mask"]).sum(1) % 97).float()
+    assert rec["sampled_inds"] == [2 * i for i in sc[::2].topk(3)[1].tolist()], (rec, sc)
 dist.destroy_process_group()
 print("OK", rank)
 """
