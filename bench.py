@@ -51,6 +51,9 @@ NCU_GEMM_DRAM_BYTES_PER_LAUNCH = {2048: (2.428e9 + 3.041e9 + 3.047e9 + 5.158e9) 
 # Per-GPU shapes of the BASELINE.json configs.  c2 is the metric's configuration (the default, the only one the
 # driver runs); the others are reported on request with the same JSON contract.
 WORKLOADS = {
+    "c1": dict(kind="mdf", clips=1, frames=64, K=16, W=8, H=224, Wd=224,
+               desc="MDF sampling of {clips} synthetic {frames}-frame 224x224 clip, K={K}, W={W}: the reference's CPU-runnable case "
+                    "(BASELINE configs[0]) as a single-clip latency probe"),
     "c2": dict(kind="mdf", clips=256, frames=128, K=16, W=8, H=224, Wd=224,
                desc="MDF batch of {clips} synthetic {frames}-frame 224x224 clips per GPU, K={K}, W={W} (BASELINE configs[1])"),
     "c3": dict(kind="mif", clips=256, frames=128, K=8, W=0, H=224, Wd=224,
