@@ -518,3 +518,10 @@ def test_generate_h5_rows_match_reference_style_loop(encoder, tmp_path):
             want = sas.sample_frames_uniform(frames, K) if strategy == "uni" else \
                 sas.sample_frame_indices(frames, K, 4, len(frames))
             assert np.array_equal(np.asarray(ds2[i]), want.reshape(K, -1).numpy()), (strategy, i)
+
+
+def test_plain_c_client_on_the_gpu(abi_check_exe):
+    """tests/c_abi/abi_check.c --gpu: selection entry points driven from C99 with cudaMalloc'd buffers."""
+    import subprocess
+    out = subprocess.run([abi_check_exe, "--gpu"], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi_check ok (gpu)" in out.stdout, out.stdout + out.stderr

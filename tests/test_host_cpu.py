@@ -252,3 +252,9 @@ def test_scorer_needs_the_gpu_no_cpu_fallback():
         pytest.skip("CPU-only check")
     with pytest.raises(Exception):
         scorer.CaptionScorer(synth.random_scorer_state_dict(vocab=32))
+
+
+def test_plain_c_client_links_and_gets_error_codes(abi_check_exe):
+    """tests/c_abi/abi_check.c (C99, knows only include/sasvqa.h): version, sizes and argument errors without a GPU."""
+    out = subprocess.run([abi_check_exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi_check ok" in out.stdout, out.stdout + out.stderr
