@@ -44,6 +44,19 @@ print(f"layernorm_bf16  {ms:.3f} ms  {n * 197 * 4608 / ms / 1e6:7.0f} GB/s  {n *
 feats = torch.nn.functional.normalize(torch.randn(B, T, 768, device="cuda"), dim=-1)
 ms = timeit(lambda: ops.mdf_scores(feats, 8))
 print(f"mdf_scores      {ms:.4f} ms  {B * T * 3076 / ms / 1e6:7.0f} GB/s")
+del feats
+# HBM-sized: 2048 clips x 128 frames of features = 805 MB (> L2), plus a long-video shape
+for Bs, Ts, Ws in ((2048, 128, 8), (256, 512, 8), (2048, 128, 4)):
+    big = torch.nn.functional.normalize(torch.randn(Bs, Ts, 768, device="cuda"), dim=-1)
+    ms = timeit(lambda: ops.mdf_scores(big, Ws))
+    gbs = Bs * Ts * 3076 / ms / 1e6
+    print(f"mdf_scores B={Bs} T={Ts} W={Ws}  {ms:.4f} ms  {gbs:7.0f} GB/s  {gbs / PEAK:.2f} of peak")
+    qb = torch.randn(Bs, 768, device="cuda")
+    ms = timeit(lambda: ops.mif_scores(big, qb))
+    gbs = Bs * Ts * 3076 / ms / 1e6
+    print(f"mif_scores B={Bs} T={Ts}      {ms:.4f} ms  {gbs:7.0f} GB/s  {gbs / PEAK:.2f} of peak")
+    del big
+feats = torch.nn.functional.normalize(torch.randn(B, T, 768, device="cuda"), dim=-1)
 q = torch.randn(B, 768, device="cuda")
 ms = timeit(lambda: ops.mif_scores(feats, q))
 print(f"mif_scores      {ms:.4f} ms  {B * T * 3076 / ms / 1e6:7.0f} GB/s")
