@@ -182,18 +182,20 @@ __global__ void __launch_bounds__(256) pre_layernorm_kernel(float* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------
 // K3a: post_layernorm on all 197 tokens (HF modeling_git.py:751) + token mean (reference
-// utils.py:44) + L2 normalise (utils.py:47, eps 1e-12).  One CTA per frame, 8 warps.
+// utils.py:44) + L2 normalise (utils.py:47, eps 1e-12).  One CTA of 4 warps per frame: with 16 such CTAs
+// resident per SM the 2048 frames of a chunk are one wave (8-warp CTAs needed two, the second 73 % full).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pool_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float* __restrict__ feats) {
-    __shared__ float part[8][kHidden];
-    __shared__ float red[8];
+constexpr int POOL_WARPS = 4;
+__global__ void __launch_bounds__(POOL_WARPS * 32) pool_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, float* __restrict__ feats) {
+    __shared__ float part[POOL_WARPS][kHidden];
+    __shared__ float red[POOL_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long frame = blockIdx.x;
     RowRegs acc;
 #pragma unroll
     for (int j = 0; j < 6; ++j) acc.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = warp; t < kTokens; t += 8) {
+    for (int t = warp; t < kTokens; t += POOL_WARPS) {
         RowRegs r;
         row_load(x + (frame * kTokens + t) * kHidden, lane, r);
         row_normalize(r, lane, gamma, beta);
@@ -208,13 +210,14 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 6; ++j) reinterpret_cast<float4*>(part[warp])[lane + 32 * j] = acc.v[j];
     __syncthreads();
-    float m[3], sq = 0.f;
+    constexpr int PER_THREAD = kHidden / (POOL_WARPS * 32);     // 6
+    float m[PER_THREAD], sq = 0.f;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
-        const int c = threadIdx.x + 256 * e;
+    for (int e = 0; e < PER_THREAD; ++e) {
+        const int c = threadIdx.x + POOL_WARPS * 32 * e;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += part[w][c];
+        for (int w = 0; w < POOL_WARPS; ++w) s += part[w][c];
         m[e] = s * (1.0f / kTokens);
         sq += m[e] * m[e];
     }
@@ -223,10 +226,10 @@ __global__ void __launch_bounds__(256) pool_norm_kernel(const float* __restrict_
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < POOL_WARPS; ++w) tot += red[w];
     const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
 #pragma unroll
-    for (int e = 0; e < 3; ++e) feats[frame * kHidden + threadIdx.x + 256 * e] = m[e] * inv;
+    for (int e = 0; e < PER_THREAD; ++e) feats[frame * kHidden + threadIdx.x + POOL_WARPS * 32 * e] = m[e] * inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -478,7 +481,7 @@ int launch_layernorm_f32(const float* x, float* out, long long rows, const float
 int launch_pool_norm(const float* x, int n_frames, const float* gamma, const float* beta, float* feats,
                      cudaStream_t s) {
     if (n_frames == 0) return 0;
-    pool_norm_kernel<<<n_frames, 256, 0, s>>>(x, gamma, beta, feats);
+    pool_norm_kernel<<<n_frames, POOL_WARPS * 32, 0, s>>>(x, gamma, beta, feats);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;
