@@ -22,24 +22,46 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __res
                          (float)(1.0 / (255.0 * (double)0.27577711f))};
     const float of[3] = {(float)(-(double)0.48145466f / (double)0.26862954f), (float)(-(double)0.4578275f / (double)0.26130258f),
                          (float)(-(double)0.40821073f / (double)0.27577711f)};
+    uint64_t sc2[3], of2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        asm("mov.b64 %0, {%1, %1};" : "=l"(sc2[c]) : "f"(sc[c]));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(of2[c]) : "f"(of[c]));
+    }
+    uint64_t kNegMagic2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(kNegMagic2) : "f"(-8388608.0f));
     const long long total = (long long)n_frames * kImg * kGrid;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    auto load = [&](long long i, uint32_t (&w)[12]) {
         const int px = (int)(i % kGrid);                         // patch column
+        const long long fy = i / kGrid;                          // frame * 224 + y
+        const uint4* src = reinterpret_cast<const uint4*>(frames + ((fy * kImg) + px * kPatch) * 3);
+        const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+        w[8] = w2.x; w[9] = w2.y; w[10] = w2.z; w[11] = w2.w;
+    };
+    auto emit = [&](long long i, const uint32_t (&w)[12]) {
+        const int px = (int)(i % kGrid);
         const long long fy = i / kGrid;
         const int y = (int)(fy % kImg);
         const long long f = fy / kImg;
-        const uint4* src = reinterpret_cast<const uint4*>(frames + ((fy * kImg) + px * kPatch) * 3);
-        const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-        const uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
         uint32_t o[3][8];                                        // [channel][pixel pair] packed bf16x2
+        // uint8 -> float without the quarter-rate I2F: PRMT drops the byte into the mantissa of 2^23 (0x4B0000uu =
+        // 8388608 + u exactly), one packed FADD2 removes the 2^23, one packed FFMA2 normalises both pixels of the pair
+        // (same values as (float)u and fmaf: the exhaustive parity check covers this path)
 #pragma unroll
         for (int p = 0; p < 16; p += 2) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const int b0 = 3 * p + c, b1 = 3 * (p + 1) + c;
-                const float u0 = (float)((w[b0 >> 2] >> ((b0 & 3) * 8)) & 0xffu), u1 = (float)((w[b1 >> 2] >> ((b1 & 3) * 8)) & 0xffu);
-                o[c][p >> 1] = pack_bf16x2(fmaf(u0, sc[c], of[c]), fmaf(u1, sc[c], of[c]));
+                const uint32_t m0 = __byte_perm(w[b0 >> 2], 0x4B000000u, 0x7440u | (uint32_t)(b0 & 3));
+                const uint32_t m1 = __byte_perm(w[b1 >> 2], 0x4B000000u, 0x7440u | (uint32_t)(b1 & 3));
+                uint64_t v;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(m0), "r"(m1));
+                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(kNegMagic2));
+                asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(sc2[c]), "l"(of2[c]));
+                float f0, f1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(v));
+                o[c][p >> 1] = pack_bf16x2(f0, f1);
             }
         }
         const long long prow = f * kPatches + (y / kPatch) * kGrid + px;
@@ -50,6 +72,22 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __res
                          "r"(o[c][0]), "r"(o[c][1]), "r"(o[c][2]), "r"(o[c][3]), "r"(o[c][4]), "r"(o[c][5]), "r"(o[c][6]),
                          "r"(o[c][7])
                          : "memory");
+    };
+    // two patch rows per thread per trip, both loads issued before either is consumed: the stage is latency-bound
+    // under the step's power-capped SM clock, so bytes in flight per SM are what buys bandwidth
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {
+        uint32_t wa[12], wb[12];
+        load(i, wa);
+        load(i + stride, wb);
+        emit(i, wa);
+        emit(i + stride, wb);
+    }
+    if (i < total) {
+        uint32_t wa[12];
+        load(i, wa);
+        emit(i, wa);
     }
 }
 
