@@ -405,16 +405,19 @@ embed_layernorm_kernel(const int32_t* __restrict__ ids, const int32_t* __restric
 }
 
 // BertPooler + classifier (modeling_bert.py:456-468, 1077-1155): logits[s] = Wc tanh(Wp x[cls(s)] + bp) + bc in
-// fp32.  One CTA per 8 sequences so that the 2.4 MB pooler matrix is streamed from L2 once per 8 rows: each warp
-// owns 96 of the 768 pooled outputs (lanes split the 768-long dot products, coalesced float4 weight loads), then
-// warp w computes the `labels` logits of sequence w.
-constexpr int POOL_SEQS = 8;
+// fp32.  One CTA per 16 sequences so that the 2.4 MB pooler matrix is streamed from L2 once per 16 rows (this
+// stage is bound by that L2 -> SM traffic: 8 rows per CTA took 4.5 ms per c3x step): each warp owns 96 of the 768
+// pooled outputs (lanes split the 768-long dot products, coalesced float4 weight loads), then the warps share out
+// the sequences for the `labels` logits.  Dynamic shared memory: cls | pooled, 2 x 16 x 768 fp32 = 96 KiB.
+constexpr int POOL_SEQS = 16;
+constexpr int POOLER_SMEM = 2 * POOL_SEQS * kHidden * (int)sizeof(float);
 __global__ void __launch_bounds__(256)
 pooler_classifier_kernel(const float* __restrict__ x, const int32_t* __restrict__ cu_seqlens, int row_base, int n_seqs,
                          const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ wc,
                          const float* __restrict__ bc, int labels, float* __restrict__ logits) {
-    __shared__ __align__(16) float cls[POOL_SEQS][kHidden];
-    __shared__ __align__(16) float pooled[POOL_SEQS][kHidden];
+    extern __shared__ __align__(16) float pool_smem[];
+    float (*cls)[kHidden] = reinterpret_cast<float (*)[kHidden]>(pool_smem);
+    float (*pooled)[kHidden] = reinterpret_cast<float (*)[kHidden]>(pool_smem + POOL_SEQS * kHidden);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s0 = blockIdx.x * POOL_SEQS;
     for (int i = threadIdx.x; i < POOL_SEQS * (kHidden / 4); i += blockDim.x) {
@@ -449,13 +452,13 @@ pooler_classifier_kernel(const float* __restrict__ x, const int32_t* __restrict_
         }
     }
     __syncthreads();
-    const int s = s0 + warp;                                  // 8 warps <-> 8 sequences
-    if (s >= n_seqs) return;
-    for (int c = 0; c < labels; ++c) {
-        float a = 0.f;
-        for (int k = lane; k < kHidden; k += 32) a = fmaf(__ldg(wc + (long long)c * kHidden + k), pooled[warp][k], a);
-        a = warp_sum(a);
-        if (lane == 0) logits[(long long)s * labels + c] = a + __ldg(bc + c);
+    for (int q = warp; q < POOL_SEQS && s0 + q < n_seqs; q += 8) {
+        for (int c = 0; c < labels; ++c) {
+            float a = 0.f;
+            for (int k = lane; k < kHidden; k += 32) a = fmaf(__ldg(wc + (long long)c * kHidden + k), pooled[q][k], a);
+            a = warp_sum(a);
+            if (lane == 0) logits[(long long)(s0 + q) * labels + c] = a + __ldg(bc + c);
+        }
     }
 }
 
@@ -578,8 +581,10 @@ int launch_pooler_classifier(const float* x, const int32_t* cu_seqlens, int row_
                              const float* bp, const float* wc, const float* bc, int labels, float* logits,
                              cudaStream_t s) {
     if (n_seqs == 0) return 0;
-    pooler_classifier_kernel<<<(n_seqs + POOL_SEQS - 1) / POOL_SEQS, 256, 0, s>>>(x, cu_seqlens, row_base, n_seqs, wp, bp,
-                                                                                   wc, bc, labels, logits);
+    static SmemAttrCache smem_attr;
+    if (int rc = smem_attr.ensure(pooler_classifier_kernel, POOLER_SMEM)) return rc;
+    pooler_classifier_kernel<<<(n_seqs + POOL_SEQS - 1) / POOL_SEQS, 256, POOLER_SMEM, s>>>(x, cu_seqlens, row_base, n_seqs,
+                                                                                             wp, bp, wc, bc, labels, logits);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;
