@@ -203,10 +203,56 @@ def cpu_reference_time(args, n_clips: int, repeats: int, warm: int, u8_clips=Non
     return times, enc_name, torch.get_num_threads(), picks, aux
 
 
+def run_reference_captions(args):
+    """Reference arm of workload c3x: the loop body of generate_inds (gen_sample.py:68-91) one QA sample at a time on the
+    host cores -- tokenizer call, HF BertForSequenceClassification forward (fp32; the restated oracle if transformers is
+    missing), the reference's strided top-K -- on a bounded sample of the GPU arm's workload."""
+    import torch
+    from oracle import bert
+    from sasvqa_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.random_scorer_state_dict()
+    try:
+        from transformers import BertConfig, BertForSequenceClassification
+        hf = BertForSequenceClassification(BertConfig(vocab_size=synth.BERT_VOCAB, num_labels=synth.BERT_LABELS)).eval()
+        hf.load_state_dict(sd, strict=False)
+        model = lambda ids, tts, msk: hf(input_ids=ids, token_type_ids=tts, attention_mask=msk)[0]   # noqa: E731
+        name = "HF BertForSequenceClassification fp32"
+    except Exception:  # noqa: BLE001
+        model = bert.BertScorerOracle(sd)
+        name = "oracle BERT restatement fp32"
+    tok = synth.SynthTokenizer()
+    n = args.cpu_clips
+    qa, caps = synth.make_qa_workload(n, args.frames, seed=synth.REF_SEED)
+    times = []
+    with torch.no_grad():
+        for it in range(max(0, min(args.warmup, 1)) + max(1, args.steps)):
+            t0 = time.perf_counter()
+            bert.generate_inds(tok, model, qa, caps, args.K, args.ds_rate)
+            if it >= max(0, min(args.warmup, 1)):
+                times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    value = n / per_step
+    sample = (f"{n} QA sample(s) x {args.frames} captions per step (bounded sample of the {args.clips}-sample batch), one sample "
+              f"per model call as the reference batches it, {name}, torch.no_grad, {torch.get_num_threads()} threads")
+    emit({
+        "impl": "reference", "metric": "MIF QA samples/sec through the caption cross-encoder", "value": value,
+        "unit": "QA samples/s", "n_gpus": args.gpus, "steps": len(times), "warmup": max(0, min(args.warmup, 1)),
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.desc.format(clips=args.clips, frames=args.frames, K=args.K, W=0), "samples_per_gpu": args.clips,
+                   "captions_per_sample": args.frames, "K": args.K},
+        "cpu_baseline": {"value": value, "unit": "QA samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "QA samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.kind == "mif-captions":
+        return run_reference_captions(args)
     times, enc_name, threads, _, _ = cpu_reference_time(args, args.cpu_clips, max(1, args.steps),
                                                         max(0, min(args.warmup, 1)))
     per_step = sum(times) / len(times)
