@@ -12,7 +12,10 @@
  * makes the copies asynchronous).  `stream` is a cudaStream_t passed as void* (NULL = default
  * stream); device-pointer entry points are asynchronous on it, host-pointer entry points return
  * after the results are in host memory.  Outputs are caller-allocated.  bf16 buffers are passed
- * as uint16_t*.  Frames are 224x224 (ViT-B/16 input of the reference's GitVisionModel) unless an entry
+ * as uint16_t*.  Threading: a handle (SasvqaEncoder / SasvqaScorer) owns one workspace and serialises its own work --
+ * call it from one thread at a time (the reference calls its sampler from the main thread only,
+ * extract_features.py:80-97); different handles, and the handle-free entry points, may be used concurrently.
+ * Frames are 224x224 (ViT-B/16 input of the reference's GitVisionModel) unless an entry
  * point takes H and W (decoded frames of any size: K0 resizes and crops them as the image processor does).
  */
 #ifndef SASVQA_H
