@@ -193,6 +193,33 @@ int sasvqa_mif_select_captions_host(SasvqaScorer* scorer, const int64_t* input_i
 int sasvqa_scorer_profile_enable(SasvqaScorer* scorer, int on);
 int sasvqa_scorer_profile_read(SasvqaScorer* scorer, double* ms_out, int64_t* scopes_out, int n_kinds);
 
+/* ---- downstream consumer, text side: the video-QA forward on the sampled frames (src/modeling/modeling.py:29-232) ----
+ * MyGitForCausalLM.forward (inference): [visual_projection(image_encoder(frame_0..K-1)) | GitEmbeddings(input_ids)]
+ * -> 6 post-LN decoder blocks under the combined mask (visual rows see visual rows; text row t sees all visual rows and
+ * text rows <= t) -> `logits = output(sequence_output)`, returned for the TEXT rows (the reference slices the visual
+ * rows' logits away, modeling.py:211-215).  The visual side runs on the SasvqaEncoder (its projection must be loaded).
+ * params_host: decoder-side entries of the model's state_dict flattened to fp32 in HF key order:
+ * git.embeddings.{word,position}_embeddings.weight, git.embeddings.LayerNorm.{weight,bias}, per layer
+ * attention.self.{query,key,value}.{weight,bias}, attention.output.dense.{weight,bias},
+ * attention.output.LayerNorm.{weight,bias}, intermediate.dense.{weight,bias}, output.dense.{weight,bias},
+ * output.LayerNorm.{weight,bias}, then output.{weight,bias} (the vocabulary head).  git-base geometry only.
+ * max_rows: rows (visual + text tokens) per pass, ~10.8 KB each; <= 0 picks the default (65 536). */
+typedef struct SasvqaGitDecoder SasvqaGitDecoder;
+uint64_t sasvqa_git_decoder_num_params(int vocab_size, int n_layers);
+int sasvqa_git_decoder_create(const float* params_host, uint64_t n_params, int vocab_size, int n_layers, int max_rows,
+                              SasvqaGitDecoder** out);
+void sasvqa_git_decoder_destroy(SasvqaGitDecoder* dec);
+int sasvqa_git_decoder_vocab_padded(const SasvqaGitDecoder* dec);   /* vocab_size rounded up to 256: the logits row stride */
+/* frames [B, K, 3, 224, 224] fp32 (rows of "sampled_frames", what the collator feeds as pixel_values), input_ids [B, L]
+ * int32 (right-padded; padded positions give rows the caller ignores) -> logits [B, L, vocab_padded] fp32, columns
+ * >= vocab_size zero.  Asynchronous on `stream`. */
+int sasvqa_git_vqa_logits_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
+                              const int32_t* input_ids_dev, int L, float* logits_dev, void* stream);
+/* inspection: fp32 stream [B*K*197 + B*L, 768] after `n_layers` blocks (all visual rows first, then all text rows);
+ * the call must fit one pass */
+int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
+                              const int32_t* input_ids_dev, int L, int n_layers, float* hidden_dev, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------
  * sasvqa_launch_count: kernels launched by this library in this process so far.
  * Profiling: when enabled, CUDA-event pairs bracket every stage launch on its stream;
@@ -217,6 +244,8 @@ int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* 
 int sasvqa_test_layernorm(const float* x_dev, int rows, const float* gamma_dev, const float* beta_dev,
                           uint16_t* out_bf16_dev, void* stream);
 /* variable-length attention of the scorer: packed qkv [M, 2304] bf16, cu_seqlens_dev [n_seqs + 1] -> out [M, 768] */
+/* attention of the GIT decoder: qkv [n*(n_vis+L), 2304] bf16 stored visual-first -> out [., 768] */
+int sasvqa_test_attention_git(const uint16_t* qkv_bf16_dev, int n_samples, int n_vis, int L, uint16_t* out_bf16_dev, void* stream);
 int sasvqa_test_attention_varlen(const uint16_t* qkv_bf16_dev, const int32_t* cu_seqlens_dev, int n_seqs, int max_len,
                                  uint16_t* out_bf16_dev, void* stream);
 

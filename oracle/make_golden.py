@@ -283,9 +283,50 @@ def gen_bert_scorer():
     np.savez_compressed(os.path.join(GOLD, "bert_scorer_hf.npz"), vocab=np.int64(SCORER_VOCAB), **out)
 
 
+def gen_git_vqa():
+    """HF GitForCausalLM (the class the reference's MyGitForCausalLM subclasses, src/modeling/modeling.py:163) with
+    num_image_with_embedding = K and its temporal embeddings ZEROED (the reference never adds them, modeling.py:87),
+    loaded with the repo's seeded encoder / projection / decoder weights, on 2 samples x 2 sampled frames."""
+    from transformers import GitConfig, GitForCausalLM
+    from oracle import git as git_oracle
+    K, L = 2, 9
+    enc_sd = synth.random_encoder_state_dict(synth.REF_SEED)
+    psd = synth.random_projection_state_dict()
+    dsd = synth.random_git_decoder_state_dict()
+    model = GitForCausalLM(GitConfig(num_image_with_embedding=K)).eval()
+    full = dict(dsd)
+    full.update({"git.image_encoder." + k: v for k, v in enc_sd.items()})
+    full.update({"git.visual_projection." + k: v for k, v in psd.items()})
+    for f in range(K):
+        full[f"git.img_temporal_embedding.{f}"] = torch.zeros(1, 1, synth.HIDDEN)
+    missing, unexpected = model.load_state_dict(full, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    frames = torch.stack([vit.image_processor_224(synth.make_clip(c, K)) for c in (60, 61)])      # [2, K, 3, 224, 224]
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(1000, synth.GIT_VOCAB, (2, L), generator=g)
+    ids[:, 0] = 101
+    mask = torch.ones(2, L, dtype=torch.long)
+    mask[1, 6:] = 0                                                 # right padding of the second question
+    ids[1, 6:] = 0
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=mask, pixel_values=frames)
+        logits = out.logits[:, K * 197:, :]                         # text rows
+        mine = git_oracle.GitVqaOracle(enc_sd, psd, dsd)(frames, ids)
+    valid = mask.bool()
+    print("git vqa: restatement vs HF max |d logit| on valid text rows:", float((mine - logits)[valid].abs().max()),
+          "| logit std", float(logits[valid].std()))
+    top = logits.topk(5, dim=-1)
+    np.savez_compressed(os.path.join(GOLD, "git_vqa_hf.npz"), clip_ids=np.asarray([60, 61]), K=np.int64(K),
+                        input_ids=ids.numpy(), attention_mask=mask.numpy(), logits_probe=logits[:, :, ::61].numpy(),
+                        logits_row=logits[0, 3].numpy(), top5_idx=top.indices.numpy(), top5_val=top.values.numpy())
+
+
 if __name__ == "__main__":
     if "--resize-only" in sys.argv:
         gen_resize()
+        sys.exit(0)
+    if "--git-only" in sys.argv:
+        gen_git_vqa()
         sys.exit(0)
     if "--scorer-only" in sys.argv:
         gen_bert_scorer()
@@ -302,3 +343,4 @@ if __name__ == "__main__":
     gen_resize()
     gen_visual_tokens()
     gen_bert_scorer()
+    gen_git_vqa()

@@ -50,6 +50,13 @@ SIGNATURES = {
     "sasvqa_mif_select_captions_host": (c_int, [_p, _p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p]),
     "sasvqa_scorer_profile_enable": (c_int, [_p, c_int]),
     "sasvqa_scorer_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
+    "sasvqa_git_decoder_num_params": (c_uint64, [c_int, c_int]),
+    "sasvqa_git_decoder_create": (c_int, [_p, c_uint64, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "sasvqa_git_decoder_destroy": (None, [_p]),
+    "sasvqa_git_decoder_vocab_padded": (c_int, [_p]),
+    "sasvqa_git_vqa_logits_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, c_int, _p, _p]),
+    "sasvqa_git_vqa_hidden_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, c_int, c_int, _p, _p]),
+    "sasvqa_test_attention_git": (c_int, [_p, c_int, c_int, c_int, _p, _p]),
     "sasvqa_test_attention_varlen": (c_int, [_p, _p, c_int, c_int, _p, _p]),
     "sasvqa_launch_count": (c_int64, []),
     "sasvqa_profile_enable": (c_int, [_p, c_int]),

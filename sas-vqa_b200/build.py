@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 # development A/B builds: SASVQA_LIB_SUFFIX=_x SASVQA_DEFINES="-DFOO=1" -> libsasvqa_b200_x.so
 SUFFIX = os.environ.get("SASVQA_LIB_SUFFIX", "")
 LIB = os.path.join(HERE, f"libsasvqa_b200{SUFFIX}.so")
-SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "attention.cu", "attention_tcgen05.cu", "elementwise.cu", "select.cu", "resize.cu", "scorer.cu"]
+SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "attention.cu", "attention_tcgen05.cu", "elementwise.cu", "select.cu", "resize.cu", "scorer.cu", "git_decoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

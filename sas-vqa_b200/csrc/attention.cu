@@ -52,7 +52,9 @@ __device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r
 template <int NT>
 __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_t k_smem, uint32_t v_smem, int key0,
                                              int lane, float (&m)[2], float (&l)[2], float (&o)[8][4],
-                                             int n_valid = kTokens) {
+                                             int n_valid = kTokens, int n_valid_hi = -1) {
+    // n_valid: keys [0, n_valid) are visible to row g of the tile; n_valid_hi (default: the same) to row g + 8
+    if (n_valid_hi < 0) n_valid_hi = n_valid;
     float s[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -75,7 +77,7 @@ __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_
         const int kcol = key0 + nt * 8 + 2 * (lane & 3);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const bool valid = (kcol + (e & 1)) < n_valid;
+            const bool valid = (kcol + (e & 1)) < ((e >> 1) ? n_valid_hi : n_valid);
             s[nt][e] = valid ? s[nt][e] * kScaleLog2 : -INFINITY;
             cmax[e >> 1] = fmaxf(cmax[e >> 1], s[nt][e]);
         }
@@ -88,7 +90,7 @@ __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_
     float alpha[2], mnew[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        mnew[r] = fmaxf(m[r], cmax[r]);              // every chunk holds >= 1 valid key, so finite
+        mnew[r] = fmaxf(m[r], cmax[r]);              // finite: a row's FIRST chunk always holds >= 1 visible key
         alpha[r] = exp2f(m[r] - mnew[r]);            // first chunk: exp2(-inf) = 0
         m[r] = mnew[r];
         l[r] *= alpha[r];
@@ -195,6 +197,122 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
         }
     }
 }
+
+// ---- attention of the downstream GIT decoder over [visual tokens | text] (HF GitSelfAttention, modeling_git.py:202-280,
+// with the mask MyGitModel.forward builds, src/modeling/modeling.py:116-140): a visual row sees the n_vis visual rows,
+// text row t sees every visual row and text rows <= t.  Both cases are "keys [0, limit(row))" with
+// limit = n_vis for visual rows and row + 1 for text rows, so the kernel is the flash loop above with a per-row limit.
+// Rows of a group of n samples are stored visual-first: sample s owns rows [s * n_vis, (s+1) * n_vis) and
+// [n * n_vis + s * L, n * n_vis + (s+1) * L).  One CTA of 8 warps per (sample, head, 128-query block); K and V stream
+// through a double-buffered shared-memory chunk of 64 keys (cp.async), warps skip chunks past their own limit.
+constexpr int GIT_WARPS = 8;
+constexpr int GIT_QBLOCK = GIT_WARPS * 16;
+
+__global__ void __launch_bounds__(GIT_WARPS * 32)
+attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_samples, int n_vis, int L,
+                     int q_blocks) {
+    __shared__ __align__(128) uint8_t kv[2][2][64 * 128];              // [buffer][K | V][64 keys x 64 d bf16]
+    const int S = n_vis + L;
+    const int qb = blockIdx.x % q_blocks;
+    const int head = (blockIdx.x / q_blocks) % kHeads;
+    const int smp = blockIdx.x / (q_blocks * kHeads);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long vis_base = (long long)smp * n_vis, txt_base = (long long)n_samples * n_vis + (long long)smp * L;
+    auto row_of = [&](int j) -> long long { return j < n_vis ? vis_base + j : txt_base + (j - n_vis); };
+    const int q0 = qb * GIT_QBLOCK;
+    const int q_last = min(q0 + GIT_QBLOCK, S) - 1;                      // last real query row of this block
+    const int block_limit = q_last < n_vis ? n_vis : q_last + 1;         // keys any row of the block can see
+    const int n_chunks = (block_limit + 63) >> 6;
+    const __nv_bfloat16* kbase = qkv + kHidden + head * kHeadDim;
+    const __nv_bfloat16* vbase = qkv + 2 * kHidden + head * kHeadDim;
+
+    auto stage = [&](int chunk, int buf) {
+        const uint32_t k_smem = (uint32_t)__cvta_generic_to_shared(kv[buf][0]);
+        const uint32_t v_smem = (uint32_t)__cvta_generic_to_shared(kv[buf][1]);
+        for (int i = threadIdx.x; i < 64 * 8; i += GIT_WARPS * 32) {
+            const int r = i >> 3, c = i & 7;
+            const long long row = row_of(min(chunk * 64 + r, S - 1));    // rows past the sequence: any real row (masked)
+            cp_async16(k_smem + tile_off(r, c), kbase + row * kQkv + c * 8);
+            cp_async16(v_smem + tile_off(r, c), vbase + row * kQkv + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // this warp's 16 query rows
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const int r0c = min(r0, S - 1), r1c = min(r1, S - 1);
+    const int lim0 = r0c < n_vis ? n_vis : r0c + 1, lim1 = r1c < n_vis ? n_vis : r1c + 1;
+    const int w_last = min(q0 + warp * 16 + 15, S - 1);
+    const int warp_limit = w_last < n_vis ? n_vis : w_last + 1;          // warp-uniform
+    const bool warp_active = q0 + warp * 16 < S;
+    uint32_t qf[4][4];
+    {
+        const __nv_bfloat16* qa = qkv + row_of(r0c) * kQkv + head * kHeadDim + 2 * t;
+        const __nv_bfloat16* qb_ = qkv + row_of(r1c) * kQkv + head * kHeadDim + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            qf[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(qa + 16 * ks));
+            qf[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(qb_ + 16 * ks));
+            qf[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(qa + 16 * ks + 8));
+            qf[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(qb_ + 16 * ks + 8));
+        }
+    }
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+
+    stage(0, 0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < n_chunks) {
+            stage(c + 1, buf ^ 1);                                       // buffer buf^1 was released by the barrier below
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                                 // chunk c is in shared memory for every warp
+        if (warp_active && c * 64 < warp_limit) {
+            const uint32_t k_smem = (uint32_t)__cvta_generic_to_shared(kv[buf][0]);
+            const uint32_t v_smem = (uint32_t)__cvta_generic_to_shared(kv[buf][1]);
+            // attend_chunk indexes keys as key0 + local column and rows of the tile in shared memory from 0
+            attend_chunk<8>(qf, k_smem - (uint32_t)(c * 64) * 128u, v_smem - (uint32_t)(c * 64) * 128u, c * 64, lane, m, l, o, lim0,
+                            lim1);
+        }
+        __syncthreads();                                                 // everyone is done with buffer buf
+    }
+    if (!warp_active) return;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+        l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+    __nv_bfloat16* o0 = out + row_of(r0c) * kHidden + head * kHeadDim + 2 * t;
+    __nv_bfloat16* o1 = out + row_of(r1c) * kHidden + head * kHeadDim + 2 * t;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+        if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+        if (r1 < S) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+    }
+}
+
+}  // namespace
+
+int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, cudaStream_t s) {
+    if (n_samples == 0) return 0;
+    SASVQA_REQUIRE(n_vis >= 1 && L >= 0, "the visual prefix must hold at least one token");
+    SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
+    const int q_blocks = (n_vis + L + GIT_QBLOCK - 1) / GIT_QBLOCK;
+    const long long grid = (long long)n_samples * kHeads * q_blocks;
+    SASVQA_REQUIRE(grid < 2147483647LL, "too many attention blocks for one launch");
+    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks);
+    SASVQA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+namespace {
 
 // ---- variable-length self-attention of the MIF cross-encoder (HF BertSelfAttention, modeling_bert.py:143-207,
 // reached from the reference at src/preprocessing/gen_sample.py:82).  Sequences are PACKED: rows

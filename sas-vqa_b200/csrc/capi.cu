@@ -26,6 +26,11 @@ int visual_tokens(SasvqaEncoder*, const uint8_t*, const float*, int, int, float*
 int mif_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, const float*, int, int, int32_t*,
                       float*, float*, float*, cudaStream_t);
 
+uint64_t git_decoder_num_params(int, int);
+int git_decoder_create(const float*, uint64_t, int, int, int, SasvqaGitDecoder**);
+void git_decoder_destroy(SasvqaGitDecoder*);
+int git_decoder_vocab_padded(const SasvqaGitDecoder*);
+int git_vqa_logits(SasvqaGitDecoder*, SasvqaEncoder*, const float*, int, int, const int32_t*, int, float*, int, float*, cudaStream_t);
 uint64_t scorer_num_params(int, int);
 int scorer_create(const float*, uint64_t, int, int, int, SasvqaScorer**);
 void scorer_destroy(SasvqaScorer*);
@@ -184,6 +189,29 @@ int sasvqa_scorer_profile_read(SasvqaScorer* scorer, double* ms, int64_t* scopes
     return scorer_profile_read(scorer, ms, scopes, n_kinds);
 }
 
+uint64_t sasvqa_git_decoder_num_params(int vocab_size, int n_layers) {
+    return vocab_size >= 1 && n_layers >= 1 ? git_decoder_num_params(vocab_size, n_layers) : 0;
+}
+int sasvqa_git_decoder_create(const float* params_host, uint64_t n_params, int vocab_size, int n_layers, int max_rows,
+                              SasvqaGitDecoder** out) {
+    return git_decoder_create(params_host, n_params, vocab_size, n_layers, max_rows, out);
+}
+void sasvqa_git_decoder_destroy(SasvqaGitDecoder* dec) { git_decoder_destroy(dec); }
+int sasvqa_git_decoder_vocab_padded(const SasvqaGitDecoder* dec) { return git_decoder_vocab_padded(dec); }
+int sasvqa_git_vqa_logits_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
+                              int L, float* logits, void* stream) {
+    SASVQA_REQUIRE(B == 0 || logits != nullptr, "null logits");
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits, dec ? 1 << 30 : 0, nullptr, S(stream));
+}
+int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
+                              int L, int n_layers, float* hidden, void* stream) {
+    SASVQA_REQUIRE(B == 0 || hidden != nullptr, "null hidden");
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, nullptr, n_layers, hidden, S(stream));
+}
+int sasvqa_test_attention_git(const uint16_t* qkv, int n_samples, int n_vis, int L, uint16_t* out, void* stream) {
+    SASVQA_REQUIRE(n_samples == 0 || (qkv && out), "null argument");
+    return launch_attention_git(CBF(qkv), BF(out), n_samples, n_vis, L, S(stream));
+}
 int sasvqa_test_attention_varlen(const uint16_t* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, uint16_t* out,
                                  void* stream) {
     SASVQA_REQUIRE(n_seqs == 0 || (qkv && cu_seqlens && out), "null argument");

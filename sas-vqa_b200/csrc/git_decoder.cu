@@ -1,0 +1,322 @@
+// Downstream consumer of the sampled frames: the video-QA forward of the reference's GIT model
+// (src/modeling/modeling.py:29-232, MyGitModel / MyGitForCausalLM over HF transformers GitModel), inference logits.
+//   visual side   per-frame image_encoder(...).last_hidden_state, concatenated, visual_projection   modeling.py:76-95
+//                 -> the sampler's own encoder kernels (encoder.cu: visual_tokens), all K frames of all samples in one batch
+//   text side     GitEmbeddings (word + position -> LayerNorm)                                       modeling.py:97-102
+//   decoder       6 post-LN BERT-style blocks over [visual rows | text rows] with the combined mask   modeling.py:114-152
+//   head          logits = output(sequence_output)                                                   modeling.py:206-207
+// git-base has the ViT's geometry (768 hidden, 12 x 64 heads, FFN 3072): every dense layer is the tcgen05 GEMM kernel.
+//
+// B200-first differences, none of which change a text-row logit:
+//  * rows of a group of samples are stored visual-first (all visual rows, then all text rows), so the encoder writes
+//    the projected visual tokens straight into the decoder's residual stream and the text rows are one contiguous
+//    A operand for the output head;
+//  * the head runs on the text rows only -- the reference also computes the K*197 visual rows' logits (97 % of that
+//    30522-wide GEMM) and slices them away (modeling.py:211-215);
+//  * the mask is never materialised: "keys [0, limit(row))" inside the attention kernel (attention.cu).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/sasvqa.h"
+#include "common.cuh"
+
+namespace sasvqa {
+
+int visual_tokens(SasvqaEncoder*, const uint8_t*, const float*, int, int, float*, cudaStream_t);
+
+namespace {
+
+constexpr float kGitLnEps = 1e-12f;
+constexpr int kGitMaxPos = 1024;
+constexpr int kGitMaxLayers = 12;
+constexpr int kDefaultMaxRows = 65536;
+
+__global__ void git_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+// fp32 rows -> bf16 rows, 8 values per thread (the visual rows the encoder wrote into the residual stream)
+__global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = src[2 * i], b = src[2 * i + 1];
+        uint4 o;
+        o.x = pack_bf16x2(a.x, a.y);
+        o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(b.x, b.y);
+        o.w = pack_bf16x2(b.z, b.w);
+        dst[i] = o;
+    }
+}
+
+struct GitLayer {
+    __nv_bfloat16 *w_qkv, *w_out, *w_fc1, *w_fc2;
+    float *b_qkv, *b_out, *ln1_g, *ln1_b, *b_fc1, *b_fc2, *ln2_g, *ln2_b;
+    CUtensorMap m_qkv, m_out, m_fc1, m_fc2;
+};
+
+}  // namespace
+
+}  // namespace sasvqa
+
+using namespace sasvqa;
+
+struct SasvqaGitDecoder {
+    int device = 0;
+    int num_sms = 148;
+    int vocab = 0, vocab_pad = 0, n_layers = 0, max_rows = 0;
+    bool use_simt = false;
+    __nv_bfloat16* arena_bf16 = nullptr;
+    float* arena_f32 = nullptr;
+    float *word = nullptr, *pos = nullptr, *emb_g = nullptr, *emb_b = nullptr, *zero_row = nullptr;
+    __nv_bfloat16* w_head = nullptr;   // [vocab_pad, 768], rows >= vocab are zero
+    float* b_head = nullptr;           // [vocab_pad]
+    CUtensorMap m_head;
+    GitLayer L[kGitMaxLayers];
+    float* x = nullptr;                // [max_rows, 768] fp32 stream
+    __nv_bfloat16* h = nullptr;        // [max_rows, 768]
+    __nv_bfloat16* big = nullptr;      // [max_rows, 3072]
+    CUtensorMap m_h, m_big_fc, m_out_qkv, m_out_fc1, m_out_x;
+    int32_t* cu_dev = nullptr;
+    size_t cu_cap = 0;
+};
+
+namespace sasvqa {
+
+namespace {
+
+int dgemm(SasvqaGitDecoder* d, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, const CUtensorMap* mo,
+          cudaStream_t s) {
+    if (d->use_simt) return launch_gemm_simt(g, s);
+    return launch_gemm_tcgen05(g, ma, mb, mo, d->num_sms, s);
+}
+
+}  // namespace
+
+uint64_t git_decoder_num_params(int vocab, int n_layers) {
+    const uint64_t H = kHidden, F = kFfn;
+    return (uint64_t)vocab * H + (uint64_t)kGitMaxPos * H + 2 * H +
+           (uint64_t)n_layers * (4 * (H * H + H) + 2 * H + (F * H + F) + (H * F + H) + 2 * H) + ((uint64_t)vocab * H + vocab);
+}
+
+void git_decoder_destroy(SasvqaGitDecoder* d) {
+    if (!d) return;
+    cudaFree(d->arena_bf16); cudaFree(d->arena_f32);
+    cudaFree(d->x); cudaFree(d->h); cudaFree(d->big); cudaFree(d->cu_dev);
+    delete d;
+}
+
+int git_decoder_create(const float* params_host, uint64_t n_params, int vocab, int n_layers, int max_rows,
+                       SasvqaGitDecoder** out) {
+    SASVQA_REQUIRE(out != nullptr && params_host != nullptr, "null argument");
+    SASVQA_REQUIRE(vocab >= 1 && n_layers >= 1 && n_layers <= kGitMaxLayers, "bad vocabulary size / layer count");
+    SASVQA_REQUIRE(n_params == git_decoder_num_params(vocab, n_layers),
+                   "state dict size does not match a git-base text decoder with this vocabulary and layer count");
+    if (max_rows <= 0) max_rows = kDefaultMaxRows;
+    SasvqaGitDecoder* d = new SasvqaGitDecoder();
+    auto fail = [&](int rc) { git_decoder_destroy(d); return rc; };
+#define TRY(expr) do { int _rc = (expr); if (_rc) return fail(_rc); } while (0)
+#define TRYCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(SASVQA_ERR_CUDA); } } while (0)
+    TRYCUDA(cudaGetDevice(&d->device));
+    cudaDeviceProp prop;
+    TRYCUDA(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10) {
+        set_last_error("sasvqa_b200 needs an sm_100a GPU (B200); found compute capability " + std::to_string(prop.major) +
+                       "." + std::to_string(prop.minor));
+        return fail(SASVQA_ERR_INVALID);
+    }
+    d->num_sms = prop.multiProcessorCount;
+    d->vocab = vocab;
+    d->vocab_pad = (vocab + 255) / 256 * 256;               // the GEMM's N tile
+    d->n_layers = n_layers;
+    d->max_rows = max_rows;
+    const char* dbg = getenv("SASVQA_DEBUG_SIMT_GEMM");
+    d->use_simt = dbg != nullptr && dbg[0] == '1';
+
+    float* raw = nullptr;
+    TRYCUDA(cudaMalloc(&raw, n_params * sizeof(float)));
+    if (cudaMemcpy(raw, params_host, n_params * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(raw);
+        set_last_error("uploading decoder parameters failed");
+        return fail(SASVQA_ERR_CUDA);
+    }
+    const size_t H = kHidden, F = kFfn;
+    const size_t n_mat = (size_t)n_layers * (4 * H * H + 2 * F * H) + (size_t)d->vocab_pad * H;
+    const size_t n_vec = (size_t)vocab * H + kGitMaxPos * H + 2 * H + H /*zero row*/ +
+                         (size_t)n_layers * (3 * H + H + 2 * H + F + H + 2 * H) + d->vocab_pad;
+    if (cudaMalloc(&d->arena_bf16, n_mat * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMalloc(&d->arena_f32, n_vec * sizeof(float)) != cudaSuccess) {
+        cudaFree(raw);
+        set_last_error("allocating decoder weights failed");
+        return fail(SASVQA_ERR_NOMEM);
+    }
+    cudaMemset(d->arena_bf16, 0, n_mat * sizeof(__nv_bfloat16));
+    cudaMemset(d->arena_f32, 0, n_vec * sizeof(float));
+    __nv_bfloat16* mp = d->arena_bf16;
+    float* vp = d->arena_f32;
+    const float* rp = raw;
+    auto take_mat = [&](size_t n) {
+        __nv_bfloat16* dst = mp;
+        git_f32_to_bf16_kernel<<<592, 256>>>(rp, dst, (long long)n);
+        mp += n; rp += n;
+        return dst;
+    };
+    auto take_vec = [&](size_t n) {
+        float* dst = vp;
+        cudaMemcpyAsync(dst, rp, n * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+        vp += n; rp += n;
+        return dst;
+    };
+    d->word = take_vec((size_t)vocab * H);
+    d->pos = take_vec((size_t)kGitMaxPos * H);
+    d->emb_g = take_vec(H);
+    d->emb_b = take_vec(H);
+    d->zero_row = vp; vp += H;                               // GIT has no token types: the embedding kernel adds this row of zeros
+    for (int l = 0; l < n_layers; ++l) {
+        GitLayer& Ly = d->L[l];
+        Ly.w_qkv = mp; mp += 3 * H * H;                      // HF order query, key, value = the fused q | k | v rows
+        Ly.b_qkv = vp; vp += 3 * H;
+        for (int j = 0; j < 3; ++j) {
+            git_f32_to_bf16_kernel<<<592, 256>>>(rp, Ly.w_qkv + j * H * H, (long long)(H * H));
+            rp += H * H;
+            cudaMemcpyAsync(Ly.b_qkv + j * H, rp, H * sizeof(float), cudaMemcpyDeviceToDevice, 0);
+            rp += H;
+        }
+        Ly.w_out = take_mat(H * H);
+        Ly.b_out = take_vec(H);
+        Ly.ln1_g = take_vec(H);
+        Ly.ln1_b = take_vec(H);
+        Ly.w_fc1 = take_mat(F * H);
+        Ly.b_fc1 = take_vec(F);
+        Ly.w_fc2 = take_mat(H * F);
+        Ly.b_fc2 = take_vec(H);
+        Ly.ln2_g = take_vec(H);
+        Ly.ln2_b = take_vec(H);
+    }
+    d->w_head = take_mat((size_t)vocab * H);
+    mp += (size_t)(d->vocab_pad - vocab) * H;                // zero rows up to the N tile
+    d->b_head = take_vec(vocab);
+    vp += d->vocab_pad - vocab;
+    cudaError_t ce = cudaDeviceSynchronize();
+    cudaFree(raw);
+    if (ce != cudaSuccess || (size_t)(rp - raw) != n_params || (size_t)(mp - d->arena_bf16) != n_mat ||
+        (size_t)(vp - d->arena_f32) != n_vec) {
+        set_last_error(std::string("decoder weight conversion failed: ") + cudaGetErrorString(ce));
+        return fail(SASVQA_ERR_CUDA);
+    }
+    const size_t rows = (size_t)max_rows;
+    if (cudaMalloc(&d->x, rows * H * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&d->h, rows * H * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMalloc(&d->big, rows * F * sizeof(__nv_bfloat16)) != cudaSuccess) {
+        set_last_error("allocating decoder workspace failed (lower max_rows)");
+        return fail(SASVQA_ERR_NOMEM);
+    }
+    TRYCUDA(cudaMemset(d->x, 0, rows * H * sizeof(float)));
+    TRYCUDA(cudaMemset(d->h, 0, rows * H * sizeof(__nv_bfloat16)));
+    TRYCUDA(cudaMemset(d->big, 0, rows * F * sizeof(__nv_bfloat16)));
+    TRY(make_tensor_map_out(&d->m_out_qkv, d->big, rows, kQkv, 0));
+    TRY(make_tensor_map_out(&d->m_out_fc1, d->big, rows, kFfn, 0));
+    TRY(make_tensor_map_out(&d->m_out_x, d->x, rows, kHidden, 1));
+    TRY(make_tensor_map_bf16_kmajor(&d->m_h, d->h, rows, kHidden, 128));
+    TRY(make_tensor_map_bf16_kmajor(&d->m_big_fc, d->big, rows, kFfn, 128));
+    TRY(make_tensor_map_bf16_kmajor(&d->m_head, d->w_head, (uint64_t)d->vocab_pad, kHidden, 128));
+    for (int l = 0; l < n_layers; ++l) {
+        GitLayer& Ly = d->L[l];
+        TRY(make_tensor_map_bf16_kmajor(&Ly.m_qkv, Ly.w_qkv, kQkv, kHidden, 128));
+        TRY(make_tensor_map_bf16_kmajor(&Ly.m_out, Ly.w_out, kHidden, kHidden, 128));
+        TRY(make_tensor_map_bf16_kmajor(&Ly.m_fc1, Ly.w_fc1, kFfn, kHidden, 128));
+        TRY(make_tensor_map_bf16_kmajor(&Ly.m_fc2, Ly.w_fc2, kHidden, kFfn, 128));
+    }
+#undef TRY
+#undef TRYCUDA
+    *out = d;
+    return 0;
+}
+
+int git_decoder_vocab_padded(const SasvqaGitDecoder* d) { return d ? d->vocab_pad : 0; }
+
+// frames [B, K, 3, 224, 224] fp32 (rows of "sampled_frames") + input_ids [B, L] int32 -> logits of the text rows
+// [B, L, vocab_pad] fp32 (columns >= vocab are zero).  hidden_or_null: [n*K*197 + n*L, 768] fp32 stream of the
+// FIRST group after n_layers blocks (inspection; visual rows first, then text rows).
+int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids, int L,
+                   float* logits, int n_layers, float* hidden_or_null, cudaStream_t s) {
+    SASVQA_REQUIRE(d != nullptr && enc != nullptr && B >= 0 && K >= 1, "bad arguments");
+    SASVQA_REQUIRE(L >= 1 && L <= kGitMaxPos, "text length must be in [1, 1024] (GIT position table)");
+    if (n_layers == 1 << 30) n_layers = d->n_layers;            // "all of them" (the logits entry point)
+    SASVQA_REQUIRE(n_layers >= 0 && n_layers <= d->n_layers, "bad layer count");
+    if (B == 0) return 0;
+    SASVQA_REQUIRE(frames != nullptr && ids != nullptr && (logits != nullptr || hidden_or_null != nullptr), "null argument");
+    const int n_vis = K * kTokens;
+    const long long S = (long long)n_vis + L;
+    SASVQA_REQUIRE(S <= d->max_rows, "one sample's sequence does not fit the decoder workspace (raise max_rows)");
+    SASVQA_REQUIRE(hidden_or_null == nullptr || (long long)B * S <= d->max_rows, "hidden-state inspection needs one pass");
+    const int group = (int)std::min<long long>(B, d->max_rows / S);
+    if ((size_t)(group + 1) * sizeof(int32_t) > d->cu_cap) {
+        if (d->cu_dev) SASVQA_CUDA_CHECK(cudaFree(d->cu_dev));
+        d->cu_dev = nullptr;
+        d->cu_cap = 0;
+        SASVQA_CUDA_CHECK(cudaMalloc((void**)&d->cu_dev, (size_t)(group + 1) * sizeof(int32_t)));
+        d->cu_cap = (size_t)(group + 1) * sizeof(int32_t);
+    }
+    std::vector<int32_t> cu((size_t)group + 1);
+    for (int b0 = 0; b0 < B; b0 += group) {
+        const int n = std::min(group, B - b0);
+        const long long rows_vis = (long long)n * n_vis, M = rows_vis + (long long)n * L;
+        int rc;
+        // visual rows: encoder + visual_projection write fp32 rows straight into the residual stream
+        if ((rc = visual_tokens(enc, nullptr, frames + (size_t)b0 * K * kFrameElems, n * K, 1, d->x, s))) return rc;
+        rows_to_bf16_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(d->x), reinterpret_cast<uint4*>(d->h),
+                                                    rows_vis * kHidden / 8);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        // text rows: row of (sample i, position p) = rows_vis + i * L + p
+        for (int i = 0; i <= n; ++i) cu[i] = (int32_t)(rows_vis + (long long)i * L);
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(d->cu_dev, cu.data(), ((size_t)n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if ((rc = launch_embed_layernorm(ids + (size_t)b0 * L, nullptr, d->cu_dev, 0, n, L, d->vocab, 1, d->word, d->pos,
+                                         d->zero_row, d->emb_g, d->emb_b, kGitLnEps, d->x, d->h, s)))
+            return rc;
+        for (int l = 0; l < n_layers; ++l) {
+            GitLayer& Ly = d->L[l];
+            GemmArgs g{};
+            g.A = d->h; g.B = Ly.w_qkv; g.M = (int)M; g.N = kQkv; g.K = kHidden;
+            g.epilogue = EPI_BIAS_BF16; g.bias = Ly.b_qkv; g.out_bf16 = d->big;
+            if ((rc = dgemm(d, g, &d->m_h, &Ly.m_qkv, &d->m_out_qkv, s))) return rc;
+            if ((rc = launch_attention_git(d->big, d->h, n, n_vis, L, s))) return rc;
+            g = GemmArgs{};
+            g.A = d->h; g.B = Ly.w_out; g.M = (int)M; g.N = kHidden; g.K = kHidden;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_out; g.out_f32 = d->x;
+            if ((rc = dgemm(d, g, &d->m_h, &Ly.m_out, &d->m_out_x, s))) return rc;
+            if ((rc = launch_layernorm_post(d->x, d->h, M, Ly.ln1_g, Ly.ln1_b, kGitLnEps, s))) return rc;
+            g = GemmArgs{};
+            g.A = d->h; g.B = Ly.w_fc1; g.M = (int)M; g.N = kFfn; g.K = kHidden;
+            g.epilogue = EPI_BIAS_ERF_GELU_BF16; g.bias = Ly.b_fc1; g.out_bf16 = d->big;
+            if ((rc = dgemm(d, g, &d->m_h, &Ly.m_fc1, &d->m_out_fc1, s))) return rc;
+            g = GemmArgs{};
+            g.A = d->big; g.B = Ly.w_fc2; g.M = (int)M; g.N = kHidden; g.K = kFfn;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_fc2; g.out_f32 = d->x;
+            if ((rc = dgemm(d, g, &d->m_big_fc, &Ly.m_fc2, &d->m_out_x, s))) return rc;
+            if ((rc = launch_layernorm_post(d->x, d->h, M, Ly.ln2_g, Ly.ln2_b, kGitLnEps, s))) return rc;
+        }
+        if (hidden_or_null && b0 == 0)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(hidden_or_null, d->x, (size_t)M * kHidden * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (logits) {
+            // output head on the text rows: they are one contiguous [n*L, 768] bf16 block of h
+            const int Mt = n * L;
+            float* out = logits + (size_t)b0 * L * d->vocab_pad;
+            SASVQA_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)Mt * d->vocab_pad * sizeof(float), s));
+            const __nv_bfloat16* a = d->h + (size_t)rows_vis * kHidden;
+            GemmArgs g{};
+            g.A = a; g.B = d->w_head; g.M = Mt; g.N = d->vocab_pad; g.K = kHidden;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = d->b_head; g.out_f32 = out;
+            CUtensorMap ma, mo;
+            if ((rc = make_tensor_map_bf16_kmajor(&ma, a, (uint64_t)Mt, kHidden, 128))) return rc;
+            if ((rc = make_tensor_map_out(&mo, out, (uint64_t)Mt, (uint64_t)d->vocab_pad, 1))) return rc;
+            if ((rc = dgemm(d, g, &ma, &d->m_head, &mo, s))) return rc;
+        }
+    }
+    return 0;
+}
+
+}  // namespace sasvqa

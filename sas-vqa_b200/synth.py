@@ -294,3 +294,61 @@ def make_qa_workload(n_samples: int, n_captions: int, seed: int = REF_SEED, min_
         qa.append({"video": i, "question": sentence(4, 10) + " ?", "answer": _WORDS[i % len(_WORDS)]})
         caps[f"video{i}"] = [sentence(min_words, max_words) for _ in range(n_captions)]
     return qa, caps
+
+
+# ---------------------------------------------------------------------------------------------
+# Downstream video-QA model (src/modeling/modeling.py: MyGitForCausalLM, git-base geometry): the text
+# side -- embeddings, 6 post-LN blocks over [visual tokens | text], output head -- with seeded weights.
+# ---------------------------------------------------------------------------------------------
+GIT_VOCAB = 30522
+GIT_MAX_POS = 1024
+GIT_LAYERS = 6
+
+
+def git_decoder_state_dict_keys(vocab: int = GIT_VOCAB, n_layers: int = GIT_LAYERS, max_pos: int = GIT_MAX_POS):
+    """Decoder-side entries of HF ``GitForCausalLM.state_dict()`` in its own order (the image encoder and the visual
+    projection sit between the embeddings and the layers there; they are loaded into the FrameEncoder)."""
+    keys = [
+        ("git.embeddings.word_embeddings.weight", (vocab, HIDDEN)),
+        ("git.embeddings.position_embeddings.weight", (max_pos, HIDDEN)),
+        ("git.embeddings.LayerNorm.weight", (HIDDEN,)),
+        ("git.embeddings.LayerNorm.bias", (HIDDEN,)),
+    ]
+    for l in range(n_layers):
+        p = f"git.encoder.layer.{l}."
+        for nm, shape in (("attention.self.query", (HIDDEN, HIDDEN)), ("attention.self.key", (HIDDEN, HIDDEN)),
+                          ("attention.self.value", (HIDDEN, HIDDEN)), ("attention.output.dense", (HIDDEN, HIDDEN))):
+            keys.append((p + nm + ".weight", shape))
+            keys.append((p + nm + ".bias", (shape[0],)))
+        keys.append((p + "attention.output.LayerNorm.weight", (HIDDEN,)))
+        keys.append((p + "attention.output.LayerNorm.bias", (HIDDEN,)))
+        keys.append((p + "intermediate.dense.weight", (FFN, HIDDEN)))
+        keys.append((p + "intermediate.dense.bias", (FFN,)))
+        keys.append((p + "output.dense.weight", (HIDDEN, FFN)))
+        keys.append((p + "output.dense.bias", (HIDDEN,)))
+        keys.append((p + "output.LayerNorm.weight", (HIDDEN,)))
+        keys.append((p + "output.LayerNorm.bias", (HIDDEN,)))
+    keys += [("output.weight", (vocab, HIDDEN)), ("output.bias", (vocab,))]
+    return keys
+
+
+def random_git_decoder_state_dict(seed: int = REF_SEED + 3, vocab: int = GIT_VOCAB, n_layers: int = GIT_LAYERS,
+                                  bf16_exact: bool = True) -> dict:
+    """Seeded random weights of the GIT text decoder + output head under HF key names (fp32, CPU); the matrices the
+    GPU keeps in bf16 (layer projections, MLP, output head) are bf16-representable with ``bf16_exact``."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    sd = {}
+    for name, shape in git_decoder_state_dict_keys(vocab, n_layers):
+        if name.endswith("LayerNorm.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif "embeddings" in name:
+            t = 0.05 * torch.randn(shape, generator=g)
+        else:
+            t = 0.04 * torch.randn(shape, generator=g)
+            if bf16_exact:
+                t = t.to(torch.bfloat16).to(torch.float32)
+        sd[name] = t.contiguous()
+    return sd

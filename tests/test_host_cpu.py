@@ -258,3 +258,16 @@ def test_plain_c_client_links_and_gets_error_codes(abi_check_exe):
     """tests/c_abi/abi_check.c (C99, knows only include/sasvqa.h): version, sizes and argument errors without a GPU."""
     out = subprocess.run([abi_check_exe], capture_output=True, text=True)
     assert out.returncode == 0 and "abi_check ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_git_decoder_state_dict_flattening_and_hf_key_order():
+    from sasvqa_b200 import vqa
+    tr = pytest.importorskip("transformers")
+    cfg = tr.GitConfig(vocab_size=64, num_hidden_layers=2)
+    model = tr.GitForCausalLM(cfg)
+    hf = [(k, tuple(v.shape)) for k, v in model.state_dict().items()
+          if v.is_floating_point() and not k.startswith(("git.image_encoder", "git.visual_projection", "git.img_temp"))]
+    assert hf == [(k, tuple(s)) for k, s in synth.git_decoder_state_dict_keys(64, 2)]
+    flat, vocab, n_layers = vqa.flatten_git_decoder_state_dict(model.state_dict())
+    assert (vocab, n_layers) == (64, 2)
+    assert flat.numel() == _capi.lib().sasvqa_git_decoder_num_params(64, 2)

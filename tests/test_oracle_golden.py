@@ -260,3 +260,21 @@ def test_bert_scorer_padding_is_invisible_in_the_oracle():
     a = model(short["input_ids"], short["token_type_ids"], short["attention_mask"])
     b = model(padded["input_ids"], padded["token_type_ids"], padded["attention_mask"])
     assert (a[0] - b[0]).abs().max().item() <= 2e-5
+
+
+def test_git_vqa_restatement_matches_hf_fixture(golden_dir):
+    """oracle/git.py (MyGitForCausalLM's inference forward, src/modeling/modeling.py:29-232) against HF GitForCausalLM's
+    own logits with the temporal embeddings zeroed (tests/golden/git_vqa_hf.npz)."""
+    from oracle import git as git_oracle, vit
+    import sasvqa_b200.synth as synth
+    g = _load(golden_dir, "git_vqa_hf.npz")
+    K = int(g["K"])
+    frames = torch.stack([vit.image_processor_224(synth.make_clip(int(c), K)) for c in g["clip_ids"]])
+    ids = torch.from_numpy(g["input_ids"])
+    mask = torch.from_numpy(g["attention_mask"]).bool()
+    model = git_oracle.GitVqaOracle(synth.random_encoder_state_dict(synth.REF_SEED), synth.random_projection_state_dict(),
+                                    synth.random_git_decoder_state_dict())
+    logits = model(frames, ids)
+    assert (logits[:, :, ::61] - torch.from_numpy(g["logits_probe"])).abs()[mask].max().item() <= 1e-4
+    assert (logits[0, 3] - torch.from_numpy(g["logits_row"])).abs().max().item() <= 1e-4
+    assert torch.equal(logits.topk(1, dim=-1).indices[..., 0][mask], torch.from_numpy(g["top5_idx"])[..., 0][mask])
