@@ -68,6 +68,10 @@ WORKLOADS = {
                desc="end to end: {clips} MSVD/MSRVTT-shaped 240x320 clips x {frames} frames per GPU (10k clips on 8 GPUs) -> "
                     "K0 resize -> MDF K={K}, W={W} -> visual tokens (encoder + GIT visual_projection) of the sampled "
                     "frames (BASELINE configs[4])"),
+    "c5x": dict(kind="mdf+vqa-full", clips=512, frames=64, K=16, W=4, H=240, Wd=320,
+                desc="end to end with the text side: {clips} MSVD/MSRVTT-shaped 240x320 clips x {frames} frames per GPU -> K0 resize "
+                     "-> MDF K={K}, W={W} -> GIT video-QA forward (encoder + visual_projection + 6 decoder blocks + vocabulary "
+                     "head, 20 question tokens) on the sampled frames (BASELINE configs[4])"),
 }
 
 
@@ -306,7 +310,12 @@ def run_ours(args):
     start, end = sharding.shard_range(n_total, rank, world)
     clips = synth.make_clips(range(start, end), T, device=dev, H=args.height, W=args.width)   # uint8, resident in HBM
     q = synth.question_embeddings(range(start, end), device=dev) if args.kind == "mif" else None
-    if args.kind == "mdf+vqa":
+    dec, qids = None, None
+    if args.kind == "mdf+vqa-full":
+        dec = sas.GitDecoder(synth.random_git_decoder_state_dict(), max_rows=131072)
+        qids = torch.randint(1000, synth.GIT_VOCAB, (B, 20), generator=torch.Generator().manual_seed(5)).to(dev)
+        vqa_ev = []
+    if args.kind in ("mdf+vqa", "mdf+vqa-full"):
         psd = synth.random_projection_state_dict()
         enc.set_projection(*[psd[f"visual_projection.{k}"] for k in ("0.weight", "0.bias", "1.weight", "1.bias")])
     torch.cuda.synchronize()
@@ -320,6 +329,14 @@ def run_ours(args):
         if args.kind == "mdf+vqa":                               # the downstream forward's visual side, 256 clips at a time
             for b0 in range(0, B, 256):
                 res["tokens_probe"] = sas.encode_sampled_frames(res["frames"][b0:b0 + 256], enc)[:, ::197, :8]
+        if args.kind == "mdf+vqa-full":                          # the whole downstream forward: next-token logits of the question
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for b0 in range(0, B, 64):
+                logits = sas.vqa_logits(res["frames"][b0:b0 + 64], qids[b0:b0 + 64], enc, dec)
+                res["answer_probe"] = logits[:, -1, :].argmax(dim=-1)
+            e1.record()
+            vqa_ev.append((e0, e1))
         table = sharding.all_gather_rows(res["indices"], n_total) if world > 1 else res["indices"]
         return res, table
 
@@ -358,7 +375,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (all five GEMM shapes run the same tcgen05 kernel)
     gemm_ms = sum(prof[k][0] for k in prof if k.startswith("gemm_"))
     gemm_launches = sum(prof[k][1] for k in prof if k.startswith("gemm_"))
-    frames_per_step = B * T + (B * K if args.kind == "mdf+vqa" else 0)      # c5 encodes the K picks a second time
+    frames_per_step = B * T + (B * K if args.kind in ("mdf+vqa", "mdf+vqa-full") else 0)   # c5 encodes the K picks a second time
     frames_timed = frames_per_step * args.steps
     achieved_tf = GEMM_FLOP_PER_FRAME * frames_timed / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
@@ -388,6 +405,13 @@ def run_ours(args):
         if prof.get(k, (0.0, 0))[0] > 0:
             gbs = per * B * args.steps / (prof[k][0] / 1e3) / 1e9
             hbm[k] = {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    if args.kind == "mdf+vqa-full":
+        torch.cuda.synchronize()
+        timed = vqa_ev[-args.steps:]
+        roofline["vqa_forward_ms_per_step"] = sum(a.elapsed_time(b) for a, b in timed) / len(timed)
+        roofline["vqa_forward_note"] = ("sas.vqa_logits over the K picks of every clip: encoder + visual_projection + 6 decoder blocks "
+                                        "over K*197 + 20 rows per clip + vocabulary head on the text rows; the GEMM roofline above "
+                                        "counts only the encoder GEMMs")
     roofline["hbm_stages"] = hbm
     roofline["hbm_peak_gbs"] = peaks["hbm"]
 
@@ -453,6 +477,8 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(line)
+    if dec is not None:
+        dec.close()
     enc.close()
     if world > 1:
         dist.destroy_process_group()
