@@ -210,10 +210,10 @@ constexpr int GIT_QBLOCK = GIT_WARPS * 16;
 
 __global__ void __launch_bounds__(GIT_WARPS * 32)
 attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_samples, int n_vis, int L,
-                     int q_blocks) {
+                     int q_blocks, int q_block0) {
     __shared__ __align__(128) uint8_t kv[2][2][64 * 128];              // [buffer][K | V][64 keys x 64 d bf16]
     const int S = n_vis + L;
-    const int qb = blockIdx.x % q_blocks;
+    const int qb = q_block0 + blockIdx.x % q_blocks;             // q_block0 > 0: only the blocks that hold text rows
     const int head = (blockIdx.x / q_blocks) % kHeads;
     const int smp = blockIdx.x / (q_blocks * kHeads);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,14 +299,20 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 }  // namespace
 
-int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, cudaStream_t s) {
+// text_only != 0: only the query blocks that contain text rows are computed (the last decoder block when nobody reads
+// the visual rows afterwards); visual rows that share a block with the first text rows are recomputed, harmlessly
+int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, int text_only,
+                         cudaStream_t s) {
     if (n_samples == 0) return 0;
     SASVQA_REQUIRE(n_vis >= 1 && L >= 0, "the visual prefix must hold at least one token");
     SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
-    const int q_blocks = (n_vis + L + GIT_QBLOCK - 1) / GIT_QBLOCK;
+    const int all_blocks = (n_vis + L + GIT_QBLOCK - 1) / GIT_QBLOCK;
+    const int q_block0 = text_only ? n_vis / GIT_QBLOCK : 0;
+    const int q_blocks = all_blocks - q_block0;
+    if (q_blocks <= 0) return 0;                                  // text_only with L == 0
     const long long grid = (long long)n_samples * kHeads * q_blocks;
     SASVQA_REQUIRE(grid < 2147483647LL, "too many attention blocks for one launch");
-    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks);
+    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks, q_block0);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

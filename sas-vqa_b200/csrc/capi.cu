@@ -210,7 +210,7 @@ int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const f
 }
 int sasvqa_test_attention_git(const uint16_t* qkv, int n_samples, int n_vis, int L, uint16_t* out, void* stream) {
     SASVQA_REQUIRE(n_samples == 0 || (qkv && out), "null argument");
-    return launch_attention_git(CBF(qkv), BF(out), n_samples, n_vis, L, S(stream));
+    return launch_attention_git(CBF(qkv), BF(out), n_samples, n_vis, L, 0, S(stream));
 }
 int sasvqa_test_attention_varlen(const uint16_t* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, uint16_t* out,
                                  void* stream) {

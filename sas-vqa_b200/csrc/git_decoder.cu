@@ -279,25 +279,41 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
             return rc;
         for (int l = 0; l < n_layers; ++l) {
             GitLayer& Ly = d->L[l];
+            // Nobody reads the visual rows after the last block when only text logits are wanted: that block still
+            // projects q|k|v for every row (text queries need the visual keys and values), then runs attention,
+            // out_proj, both LayerNorms and the MLP on the text rows alone -- 1/6 of the visual-row attention and
+            // 3/4 of one block's GEMM FLOPs never happen.  The text rows are contiguous (visual-first layout).
+            const bool text_only = hidden_or_null == nullptr && l == n_layers - 1 && l == d->n_layers - 1;
+            const long long r0 = text_only ? rows_vis : 0, Mr = M - r0;
+            CUtensorMap ma_h = d->m_h, ma_big = d->m_big_fc, mo_x = d->m_out_x, mo_fc1 = d->m_out_fc1;
+            if (text_only) {
+                if ((rc = make_tensor_map_bf16_kmajor(&ma_h, d->h + (size_t)r0 * kHidden, (uint64_t)Mr, kHidden, 128))) return rc;
+                if ((rc = make_tensor_map_bf16_kmajor(&ma_big, d->big + (size_t)r0 * kFfn, (uint64_t)Mr, kFfn, 128))) return rc;
+                if ((rc = make_tensor_map_out(&mo_x, d->x + (size_t)r0 * kHidden, (uint64_t)Mr, kHidden, 1))) return rc;
+                if ((rc = make_tensor_map_out(&mo_fc1, d->big + (size_t)r0 * kFfn, (uint64_t)Mr, kFfn, 0))) return rc;
+            }
+            float* xr = d->x + (size_t)r0 * kHidden;
+            __nv_bfloat16* hr = d->h + (size_t)r0 * kHidden;
+            __nv_bfloat16* bigr = d->big + (size_t)r0 * kFfn;
             GemmArgs g{};
             g.A = d->h; g.B = Ly.w_qkv; g.M = (int)M; g.N = kQkv; g.K = kHidden;
             g.epilogue = EPI_BIAS_BF16; g.bias = Ly.b_qkv; g.out_bf16 = d->big;
             if ((rc = dgemm(d, g, &d->m_h, &Ly.m_qkv, &d->m_out_qkv, s))) return rc;
-            if ((rc = launch_attention_git(d->big, d->h, n, n_vis, L, s))) return rc;
+            if ((rc = launch_attention_git(d->big, d->h, n, n_vis, L, text_only ? 1 : 0, s))) return rc;
             g = GemmArgs{};
-            g.A = d->h; g.B = Ly.w_out; g.M = (int)M; g.N = kHidden; g.K = kHidden;
-            g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_out; g.out_f32 = d->x;
-            if ((rc = dgemm(d, g, &d->m_h, &Ly.m_out, &d->m_out_x, s))) return rc;
-            if ((rc = launch_layernorm_post(d->x, d->h, M, Ly.ln1_g, Ly.ln1_b, kGitLnEps, s))) return rc;
+            g.A = hr; g.B = Ly.w_out; g.M = (int)Mr; g.N = kHidden; g.K = kHidden;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_out; g.out_f32 = xr;
+            if ((rc = dgemm(d, g, &ma_h, &Ly.m_out, &mo_x, s))) return rc;
+            if ((rc = launch_layernorm_post(xr, hr, Mr, Ly.ln1_g, Ly.ln1_b, kGitLnEps, s))) return rc;
             g = GemmArgs{};
-            g.A = d->h; g.B = Ly.w_fc1; g.M = (int)M; g.N = kFfn; g.K = kHidden;
-            g.epilogue = EPI_BIAS_ERF_GELU_BF16; g.bias = Ly.b_fc1; g.out_bf16 = d->big;
-            if ((rc = dgemm(d, g, &d->m_h, &Ly.m_fc1, &d->m_out_fc1, s))) return rc;
+            g.A = hr; g.B = Ly.w_fc1; g.M = (int)Mr; g.N = kFfn; g.K = kHidden;
+            g.epilogue = EPI_BIAS_ERF_GELU_BF16; g.bias = Ly.b_fc1; g.out_bf16 = bigr;
+            if ((rc = dgemm(d, g, &ma_h, &Ly.m_fc1, &mo_fc1, s))) return rc;
             g = GemmArgs{};
-            g.A = d->big; g.B = Ly.w_fc2; g.M = (int)M; g.N = kHidden; g.K = kFfn;
-            g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_fc2; g.out_f32 = d->x;
-            if ((rc = dgemm(d, g, &d->m_big_fc, &Ly.m_fc2, &d->m_out_x, s))) return rc;
-            if ((rc = launch_layernorm_post(d->x, d->h, M, Ly.ln2_g, Ly.ln2_b, kGitLnEps, s))) return rc;
+            g.A = bigr; g.B = Ly.w_fc2; g.M = (int)Mr; g.N = kHidden; g.K = kFfn;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_fc2; g.out_f32 = xr;
+            if ((rc = dgemm(d, g, &ma_big, &Ly.m_fc2, &mo_x, s))) return rc;
+            if ((rc = launch_layernorm_post(xr, hr, Mr, Ly.ln2_g, Ly.ln2_b, kGitLnEps, s))) return rc;
         }
         if (hidden_or_null && b0 == 0)
             SASVQA_CUDA_CHECK(cudaMemcpyAsync(hidden_or_null, d->x, (size_t)M * kHidden * sizeof(float), cudaMemcpyDeviceToDevice, s));
