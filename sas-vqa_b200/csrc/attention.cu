@@ -208,7 +208,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 constexpr int GIT_WARPS = 8;
 constexpr int GIT_QBLOCK = GIT_WARPS * 16;
 
-__global__ void __launch_bounds__(GIT_WARPS * 32)
+__global__ void __launch_bounds__(GIT_WARPS * 32, 2)
 attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_samples, int n_vis, int L,
                      int q_blocks, int q_block0) {
     __shared__ __align__(128) uint8_t kv[2][2][64 * 128];              // [buffer][K | V][64 keys x 64 d bf16]
