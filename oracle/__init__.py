@@ -20,6 +20,9 @@ What it restates (reference = Clement25/SAS-VQA, read-only at /root/reference):
   ``BertForSequenceClassification`` for a bert-base-cased checkpoint; math at
   ``transformers/models/bert/modeling_bert.py``) and the ``generate_inds`` loop body around it; pinned
   against HF itself with seeded random weights (``tests/golden/bert_scorer_hf.npz``).
+* ``oracle.git`` -- the downstream video-QA forward on the sampled frames (``src/modeling/modeling.py:29-232``,
+  ``MyGitModel`` / ``MyGitForCausalLM`` over HF ``GitModel``): inference logits of the text rows; pinned against HF
+  ``GitForCausalLM`` with zeroed temporal embeddings (``tests/golden/git_vqa_hf.npz``).
 * ``oracle.resize`` -- the image processor's shortest-edge bicubic resize + centre crop
   (``prefetch_loader.py:74-75`` -> HF ``CLIPImageProcessor`` -> ATen uint8 resampler).
 
