@@ -44,6 +44,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {          // one MUFU op, no range fix-ups (arguments are <= 0)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // byte offset of 16-byte chunk `c` (0..7) of row `r` in a [rows][64] bf16 tile, XOR-swizzled so
 // that ldmatrix (8 rows x 16 B) is bank-conflict free
 __device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
@@ -70,17 +76,24 @@ __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_
             mma_bf16(s[nt], qf[half * 2 + 1], b2, b3);
         }
     }
-    // ---- scale, mask padded keys, chunk row maxima (rows g and g+8)
+    // ---- mask invisible keys (only chunks that reach past a row's limit pay for it), chunk row maxima of the RAW
+    // scores (rows g and g+8); the 1/8 * log2(e) scale is folded into the exponent's FFMA below
     float cmax[2] = {-INFINITY, -INFINITY};
+    if (key0 + NT * 8 > min(n_valid, n_valid_hi)) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int kcol = key0 + nt * 8 + 2 * (lane & 3);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool valid = (kcol + (e & 1)) < ((e >> 1) ? n_valid_hi : n_valid);
+                s[nt][e] = valid ? s[nt][e] : -INFINITY;
+            }
+        }
+    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int kcol = key0 + nt * 8 + 2 * (lane & 3);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool valid = (kcol + (e & 1)) < ((e >> 1) ? n_valid_hi : n_valid);
-            s[nt][e] = valid ? s[nt][e] * kScaleLog2 : -INFINITY;
-            cmax[e >> 1] = fmaxf(cmax[e >> 1], s[nt][e]);
-        }
+        cmax[0] = fmaxf(cmax[0], fmaxf(s[nt][0], s[nt][1]));
+        cmax[1] = fmaxf(cmax[1], fmaxf(s[nt][2], s[nt][3]));
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -90,19 +103,23 @@ __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_
     float alpha[2], mnew[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        mnew[r] = fmaxf(m[r], cmax[r]);              // finite: a row's FIRST chunk always holds >= 1 visible key
-        alpha[r] = exp2f(m[r] - mnew[r]);            // first chunk: exp2(-inf) = 0
+        mnew[r] = fmaxf(m[r], cmax[r] * kScaleLog2);  // finite: a row's FIRST chunk always holds >= 1 visible key
+        alpha[r] = ex2_approx(m[r] - mnew[r]);        // first chunk: exp2(-inf) = 0
         m[r] = mnew[r];
         l[r] *= alpha[r];
     }
+    // rescale the accumulator only when some row's maximum moved (alpha == 1 exactly otherwise: a bit-identical skip;
+    // after the first few chunks of a long key range that is most of the time)
+    if (__any_sync(0xffffffffu, alpha[0] != 1.0f || alpha[1] != 1.0f)) {
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-        o[dt][0] *= alpha[0];
-        o[dt][1] *= alpha[0];
-        o[dt][2] *= alpha[1];
-        o[dt][3] *= alpha[1];
+        for (int dt = 0; dt < 8; ++dt) {
+            o[dt][0] *= alpha[0];
+            o[dt][1] *= alpha[0];
+            o[dt][2] *= alpha[1];
+            o[dt][3] *= alpha[1];
+        }
     }
-    // ---- P = exp2(S - m), packed to bf16 A fragments; O += P V
+    // ---- P = exp2(S * scale - m), packed to bf16 A fragments; O += P V
 #pragma unroll
     for (int kk = 0; kk < NT / 2; ++kk) {
         uint32_t pa[4];
@@ -111,7 +128,7 @@ __device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_
         for (int j = 0; j < 2; ++j) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                p[j][e] = exp2f(s[2 * kk + j][e] - mnew[e >> 1]);
+                p[j][e] = ex2_approx(fmaf(s[2 * kk + j][e], kScaleLog2, -mnew[e >> 1]));   // masked: fma(-inf) = -inf -> 0
                 l[e >> 1] += p[j][e];
             }
         }
