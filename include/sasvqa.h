@@ -215,6 +215,12 @@ int sasvqa_git_decoder_vocab_padded(const SasvqaGitDecoder* dec);   /* vocab_siz
  * >= vocab_size zero.  Asynchronous on `stream`. */
 int sasvqa_git_vqa_logits_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
                               const int32_t* input_ids_dev, int L, float* logits_dev, void* stream);
+/* the same forward with `labels` [B, L] int32 (-100 = ignore): loss[0] = CrossEntropyLoss()(logits[:, :-1], labels[:, 1:]),
+ * the next-token objective of MyGitForCausalLM.forward (modeling.py:208-215; mean over the labels that are not ignored,
+ * NaN when there is none, as torch).  logits_or_null: also return the logits [B, L, vocab_padded]. */
+int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
+                            const int32_t* input_ids_dev, const int32_t* labels_dev, int L, float* loss_dev,
+                            float* logits_or_null_dev, void* stream);
 /* inspection: fp32 stream [B*K*197 + B*L, 768] after `n_layers` blocks (all visual rows first, then all text rows);
  * the call must fit one pass */
 int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,

@@ -81,3 +81,12 @@ class GitVqaOracle:
     def __call__(self, pixel_values: torch.Tensor, input_ids: torch.Tensor) -> torch.Tensor:
         x, Nv = self.hidden_states(pixel_values, input_ids)
         return F.linear(x[:, Nv:], self.w["output.weight"], self.w["output.bias"])      # modeling.py:207, text rows
+
+    @torch.no_grad()
+    def loss(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """``modeling.py:208-215``: next-token prediction -- ``shifted_logits = logits[:, num_image_tokens:-1]``,
+        ``labels = labels[:, 1:]``, ``CrossEntropyLoss()`` (mean, ignore_index -100)."""
+        logits = self(pixel_values, input_ids)
+        shifted = logits[:, :-1, :].contiguous()
+        tgt = torch.as_tensor(labels).long()[:, 1:].contiguous()
+        return F.cross_entropy(shifted.view(-1, shifted.shape[-1]), tgt.view(-1))

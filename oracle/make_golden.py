@@ -315,8 +315,16 @@ def gen_git_vqa():
     valid = mask.bool()
     print("git vqa: restatement vs HF max |d logit| on valid text rows:", float((mine - logits)[valid].abs().max()),
           "| logit std", float(logits[valid].std()))
+    # the reference's loss expression (modeling.py:208-215) evaluated verbatim on HF's logits (HF 5.5's own GitForCausalLM
+    # loss shifts a second time inside its loss_function, so it is not the reference's objective)
+    labels = ids.clone()
+    labels[~valid] = -100
+    with torch.no_grad():
+        shifted_logits = out.logits[:, K * 197:-1, :].contiguous()
+        loss = torch.nn.CrossEntropyLoss()(shifted_logits.view(-1, synth.GIT_VOCAB), labels[:, 1:].contiguous().view(-1))
+        print("git vqa: loss", float(loss), "restatement", float(git_oracle.GitVqaOracle(enc_sd, psd, dsd).loss(frames, ids, labels)))
     top = logits.topk(5, dim=-1)
-    np.savez_compressed(os.path.join(GOLD, "git_vqa_hf.npz"), clip_ids=np.asarray([60, 61]), K=np.int64(K),
+    np.savez_compressed(os.path.join(GOLD, "git_vqa_hf.npz"), labels=labels.numpy(), loss=np.float32(loss), clip_ids=np.asarray([60, 61]), K=np.int64(K),
                         input_ids=ids.numpy(), attention_mask=mask.numpy(), logits_probe=logits[:, :, ::61].numpy(),
                         logits_row=logits[0, 3].numpy(), top5_idx=top.indices.numpy(), top5_val=top.values.numpy())
 

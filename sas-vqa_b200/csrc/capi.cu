@@ -30,7 +30,8 @@ uint64_t git_decoder_num_params(int, int);
 int git_decoder_create(const float*, uint64_t, int, int, int, SasvqaGitDecoder**);
 void git_decoder_destroy(SasvqaGitDecoder*);
 int git_decoder_vocab_padded(const SasvqaGitDecoder*);
-int git_vqa_logits(SasvqaGitDecoder*, SasvqaEncoder*, const float*, int, int, const int32_t*, int, float*, int, float*, cudaStream_t);
+int git_vqa_logits(SasvqaGitDecoder*, SasvqaEncoder*, const float*, int, int, const int32_t*, int, float*, int, float*,
+                   const int32_t*, float*, cudaStream_t);
 uint64_t scorer_num_params(int, int);
 int scorer_create(const float*, uint64_t, int, int, int, SasvqaScorer**);
 void scorer_destroy(SasvqaScorer*);
@@ -201,12 +202,18 @@ int sasvqa_git_decoder_vocab_padded(const SasvqaGitDecoder* dec) { return git_de
 int sasvqa_git_vqa_logits_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
                               int L, float* logits, void* stream) {
     SASVQA_REQUIRE(B == 0 || logits != nullptr, "null logits");
-    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits, dec ? 1 << 30 : 0, nullptr, S(stream));
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits, 1 << 30, nullptr, nullptr, nullptr, S(stream));
 }
 int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
                               int L, int n_layers, float* hidden, void* stream) {
     SASVQA_REQUIRE(B == 0 || hidden != nullptr, "null hidden");
-    return git_vqa_logits(dec, enc, frames, B, K, ids, L, nullptr, n_layers, hidden, S(stream));
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, nullptr, n_layers, hidden, nullptr, nullptr, S(stream));
+}
+int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
+                            const int32_t* labels, int L, float* loss, float* logits_or_null, void* stream) {
+    SASVQA_REQUIRE(loss != nullptr && labels != nullptr, "null loss / labels");
+    SASVQA_REQUIRE(B >= 1, "the loss of an empty batch is undefined");
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits_or_null, 1 << 30, nullptr, labels, loss, S(stream));
 }
 int sasvqa_test_attention_git(const uint16_t* qkv, int n_samples, int n_vis, int L, uint16_t* out, void* stream) {
     SASVQA_REQUIRE(n_samples == 0 || (qkv && out), "null argument");

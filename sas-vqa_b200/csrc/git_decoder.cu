@@ -51,6 +51,81 @@ __global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float4* __restr
     }
 }
 
+// Next-token cross-entropy of the text rows (MyGitForCausalLM.forward, modeling.py:208-215: logits[:, n_vis:-1] against
+// labels[:, 1:], nn.CrossEntropyLoss defaults = mean over labels != -100).  One CTA per (sample, position < L - 1):
+// a single pass keeps a running (max, sum of exp) per thread, a block reduction combines them, thread 0 writes
+// logsumexp - logit[label].  A second one-CTA kernel sums the rows in a fixed order (no atomics: run-to-run identical).
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, int vocab, int vocab_pad, int L,
+                                                       const int32_t* __restrict__ labels, float* __restrict__ row_loss,
+                                                       int32_t* __restrict__ row_valid) {
+    __shared__ float sm[8], ss[8];
+    const int b = blockIdx.x / (L - 1), t = blockIdx.x - b * (L - 1);
+    const int label = labels[(long long)b * L + t + 1];
+    if (label < 0 || label >= vocab) {                       // ignore_index (-100); out-of-range labels are ignored too
+        if (threadIdx.x == 0) {
+            row_loss[blockIdx.x] = 0.f;
+            row_valid[blockIdx.x] = 0;
+        }
+        return;
+    }
+    const float* row = logits + ((long long)b * L + t) * vocab_pad;
+    float m = -INFINITY, sum = 0.f;
+    for (int i = threadIdx.x; i < vocab; i += 256) {
+        const float v = row[i];
+        if (v > m) {
+            sum = sum * __expf(m - v) + 1.f;
+            m = v;
+        } else {
+            sum += __expf(v - m);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mn = fmaxf(m, m2);
+        sum = (m == -INFINITY ? 0.f : sum * __expf(m - mn)) + (m2 == -INFINITY ? 0.f : s2 * __expf(m2 - mn));
+        m = mn;
+    }
+    if (lane == 0) {
+        sm[warp] = m;
+        ss[warp] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mt = sm[0], st = ss[0];
+        for (int w = 1; w < 8; ++w) {
+            const float mn = fmaxf(mt, sm[w]);
+            st = (mt == -INFINITY ? 0.f : st * __expf(mt - mn)) + (sm[w] == -INFINITY ? 0.f : ss[w] * __expf(sm[w] - mn));
+            mt = mn;
+        }
+        row_loss[blockIdx.x] = (mt + logf(st)) - row[label];
+        row_valid[blockIdx.x] = 1;
+    }
+}
+__global__ void __launch_bounds__(256) ce_mean_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_valid,
+                                                       int n, float* __restrict__ loss) {
+    __shared__ double acc[256];
+    __shared__ int cnt[256];
+    double a = 0.0;
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        a += (double)row_loss[i];
+        c += row_valid[i];
+    }
+    acc[threadIdx.x] = a;
+    cnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            acc[threadIdx.x] += acc[threadIdx.x + o];
+            cnt[threadIdx.x] += cnt[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(acc[0] / (double)cnt[0]);      // no valid label: 0 / 0 = NaN, as torch
+}
+
 struct GitLayer {
     __nv_bfloat16 *w_qkv, *w_out, *w_fc1, *w_fc2;
     float *b_qkv, *b_out, *ln1_g, *ln1_b, *b_fc1, *b_fc2, *ln2_g, *ln2_b;
@@ -81,11 +156,28 @@ struct SasvqaGitDecoder {
     CUtensorMap m_h, m_big_fc, m_out_qkv, m_out_fc1, m_out_x;
     int32_t* cu_dev = nullptr;
     size_t cu_cap = 0;
+    // loss path scratch: logits of one group, per-row losses of the whole call
+    float* logits_scratch = nullptr;
+    size_t logits_cap = 0;
+    float* row_loss = nullptr;
+    size_t row_loss_cap = 0;
+    int32_t* row_valid = nullptr;
+    size_t row_valid_cap = 0;
 };
 
 namespace sasvqa {
 
 namespace {
+
+int dgrow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) SASVQA_CUDA_CHECK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    SASVQA_CUDA_CHECK(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
 
 int dgemm(SasvqaGitDecoder* d, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, const CUtensorMap* mo,
           cudaStream_t s) {
@@ -105,6 +197,7 @@ void git_decoder_destroy(SasvqaGitDecoder* d) {
     if (!d) return;
     cudaFree(d->arena_bf16); cudaFree(d->arena_f32);
     cudaFree(d->x); cudaFree(d->h); cudaFree(d->big); cudaFree(d->cu_dev);
+    cudaFree(d->logits_scratch); cudaFree(d->row_loss); cudaFree(d->row_valid);
     delete d;
 }
 
@@ -240,14 +333,20 @@ int git_decoder_vocab_padded(const SasvqaGitDecoder* d) { return d ? d->vocab_pa
 // frames [B, K, 3, 224, 224] fp32 (rows of "sampled_frames") + input_ids [B, L] int32 -> logits of the text rows
 // [B, L, vocab_pad] fp32 (columns >= vocab are zero).  hidden_or_null: [n*K*197 + n*L, 768] fp32 stream of the
 // FIRST group after n_layers blocks (inspection; visual rows first, then text rows).
+// labels_or_null [B, L] int32 + loss_or_null [1]: the mean next-token cross-entropy of modeling.py:208-215 (labels of -100
+// are ignored); logits may then be NULL (a per-group scratch holds them).
 int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids, int L,
-                   float* logits, int n_layers, float* hidden_or_null, cudaStream_t s) {
+                   float* logits, int n_layers, float* hidden_or_null, const int32_t* labels_or_null, float* loss_or_null,
+                   cudaStream_t s) {
     SASVQA_REQUIRE(d != nullptr && enc != nullptr && B >= 0 && K >= 1, "bad arguments");
     SASVQA_REQUIRE(L >= 1 && L <= kGitMaxPos, "text length must be in [1, 1024] (GIT position table)");
     if (n_layers == 1 << 30) n_layers = d->n_layers;            // "all of them" (the logits entry point)
     SASVQA_REQUIRE(n_layers >= 0 && n_layers <= d->n_layers, "bad layer count");
     if (B == 0) return 0;
-    SASVQA_REQUIRE(frames != nullptr && ids != nullptr && (logits != nullptr || hidden_or_null != nullptr), "null argument");
+    const bool want_loss = loss_or_null != nullptr;
+    SASVQA_REQUIRE(!want_loss || (labels_or_null != nullptr && L >= 2), "the loss needs labels and at least two text positions");
+    SASVQA_REQUIRE(frames != nullptr && ids != nullptr && (logits != nullptr || hidden_or_null != nullptr || want_loss),
+                   "null argument");
     const int n_vis = K * kTokens;
     const long long S = (long long)n_vis + L;
     SASVQA_REQUIRE(S <= d->max_rows, "one sample's sequence does not fit the decoder workspace (raise max_rows)");
@@ -259,6 +358,13 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
         d->cu_cap = 0;
         SASVQA_CUDA_CHECK(cudaMalloc((void**)&d->cu_dev, (size_t)(group + 1) * sizeof(int32_t)));
         d->cu_cap = (size_t)(group + 1) * sizeof(int32_t);
+    }
+    if (want_loss) {
+        int rc;
+        if ((rc = dgrow((void**)&d->row_loss, &d->row_loss_cap, (size_t)B * (L - 1) * sizeof(float)))) return rc;
+        if ((rc = dgrow((void**)&d->row_valid, &d->row_valid_cap, (size_t)B * (L - 1) * sizeof(int32_t)))) return rc;
+        if (!logits && (rc = dgrow((void**)&d->logits_scratch, &d->logits_cap, (size_t)group * L * d->vocab_pad * sizeof(float))))
+            return rc;
     }
     std::vector<int32_t> cu((size_t)group + 1);
     for (int b0 = 0; b0 < B; b0 += group) {
@@ -317,10 +423,10 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
         }
         if (hidden_or_null && b0 == 0)
             SASVQA_CUDA_CHECK(cudaMemcpyAsync(hidden_or_null, d->x, (size_t)M * kHidden * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (logits) {
+        if (logits || want_loss) {
             // output head on the text rows: they are one contiguous [n*L, 768] bf16 block of h
             const int Mt = n * L;
-            float* out = logits + (size_t)b0 * L * d->vocab_pad;
+            float* out = logits ? logits + (size_t)b0 * L * d->vocab_pad : d->logits_scratch;
             SASVQA_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)Mt * d->vocab_pad * sizeof(float), s));
             const __nv_bfloat16* a = d->h + (size_t)rows_vis * kHidden;
             GemmArgs g{};
@@ -330,7 +436,18 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
             if ((rc = make_tensor_map_bf16_kmajor(&ma, a, (uint64_t)Mt, kHidden, 128))) return rc;
             if ((rc = make_tensor_map_out(&mo, out, (uint64_t)Mt, (uint64_t)d->vocab_pad, 1))) return rc;
             if ((rc = dgemm(d, g, &ma, &d->m_head, &mo, s))) return rc;
+            if (want_loss) {
+                ce_rows_kernel<<<n * (L - 1), 256, 0, s>>>(out, d->vocab, d->vocab_pad, L, labels_or_null + (size_t)b0 * L,
+                                                           d->row_loss + (size_t)b0 * (L - 1), d->row_valid + (size_t)b0 * (L - 1));
+                SASVQA_CUDA_CHECK(cudaGetLastError());
+                count_launch();
+            }
         }
+    }
+    if (want_loss) {
+        ce_mean_kernel<<<1, 256, 0, s>>>(d->row_loss, d->row_valid, B * (L - 1), loss_or_null);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
     }
     return 0;
 }

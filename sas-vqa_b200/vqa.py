@@ -92,6 +92,25 @@ def vqa_logits(pixel_values: torch.Tensor, input_ids: torch.Tensor, enc: FrameEn
     return out[:, :, :dec.vocab]
 
 
+def vqa_loss(pixel_values: torch.Tensor, input_ids: torch.Tensor, labels: torch.Tensor, enc: FrameEncoder, dec: GitDecoder,
+             want_logits: bool = False):
+    """``MyGitForCausalLM(input_ids=..., pixel_values=..., labels=...).loss`` (modeling.py:208-215): the mean next-token
+    cross-entropy over the text rows, labels of -100 ignored; a 0-d fp32 tensor on the GPU (plus the logits on request)."""
+    px, ids = _prep(enc, pixel_values, input_ids)
+    if tuple(labels.shape) != tuple(input_ids.shape):
+        raise ValueError(f"labels must have the shape of input_ids {tuple(input_ids.shape)}, got {tuple(labels.shape)}")
+    lab = labels.to(device=enc.device, dtype=torch.int32).contiguous()
+    B, K = int(px.shape[0]), int(px.shape[1])
+    L = int(ids.shape[1])
+    loss = torch.empty(1, dtype=torch.float32, device=enc.device)
+    logits = torch.empty(B, L, dec.vocab_padded, dtype=torch.float32, device=enc.device) if want_logits else None
+    with torch.cuda.device(enc.device):
+        _capi.check(_capi.lib().sasvqa_git_vqa_loss_f32(dec.handle, enc.handle, px.data_ptr(), B, K, ids.data_ptr(), lab.data_ptr(),
+                                                        L, loss.data_ptr(), _capi.ptr(logits),
+                                                        torch.cuda.current_stream().cuda_stream), "sasvqa_git_vqa_loss_f32")
+    return (loss[0], logits[:, :, :dec.vocab]) if want_logits else loss[0]
+
+
 def vqa_hidden(pixel_values: torch.Tensor, input_ids: torch.Tensor, enc: FrameEncoder, dec: GitDecoder, n_layers: int):
     """Inspection: (visual [B, K*197, 768], text [B, L, 768]) fp32 stream after ``n_layers`` decoder blocks."""
     px, ids = _prep(enc, pixel_values, input_ids)

@@ -114,3 +114,25 @@ def test_vqa_grouping_is_invisible_and_errors(models, weights):
         sas.vqa_logits(frames[:, 0], ids, enc, dec)                                   # rank 4
     with pytest.raises(sas.SasvqaError):
         sas.vqa_logits(frames, torch.zeros(5, 1025, dtype=torch.long), enc, dec)      # beyond the position table
+
+
+def test_vqa_loss_vs_reference_expression_on_hf_logits(models, weights, golden_dir):
+    """loss of MyGitForCausalLM.forward (modeling.py:208-215): fixture = the reference's expression on HF's logits."""
+    enc, dec = models
+    g = np.load(os.path.join(golden_dir, "git_vqa_hf.npz"))
+    K = int(g["K"])
+    frames = torch.stack([vit.image_processor_224(synth.make_clip(int(c), K)) for c in g["clip_ids"]])
+    ids, labels = torch.from_numpy(g["input_ids"]), torch.from_numpy(g["labels"])
+    loss, logits = vqa.vqa_loss(frames, ids, labels, enc, dec, want_logits=True)
+    assert abs(float(loss) - float(g["loss"])) <= 3e-2, (float(loss), float(g["loss"]))
+    assert torch.equal(logits, sas.vqa_logits(frames, ids, enc, dec))
+    # the kernel's reduction against torch on the very same logits: fp32 rounding only
+    want = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, dec.vocab), labels[:, 1:].reshape(-1).to(DEV))
+    assert abs(float(loss) - float(want)) <= 1e-4
+    assert float(vqa.vqa_loss(frames, ids, labels, enc, dec)) == float(loss)              # scratch-logits path, same value
+    small = vqa.GitDecoder(weights[2], max_rows=500)                                         # one sample per pass
+    try:
+        assert float(vqa.vqa_loss(frames, ids, labels, enc, small)) == float(loss)
+    finally:
+        small.close()
+    assert torch.isnan(vqa.vqa_loss(frames, ids, torch.full_like(labels, -100), enc, dec))   # nothing to predict: 0 / 0, as torch
