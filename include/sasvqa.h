@@ -127,6 +127,17 @@ int sasvqa_mdf_sample_f32(SasvqaEncoder* enc, const float* clips_chw_dev, int B,
                           int32_t* idx_dev, int32_t* status_dev, float* lcl_avg_or_null_dev,
                           float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
 
+/* ---- whole path, RAGGED batch: B clips of different lengths packed back to back --------------------------------
+ * frames [sum T, H, W, 3] uint8, clip b = frames [clip_offsets_host[b], clip_offsets_host[b+1]) (offsets start at 0).
+ * Per clip exactly what the calls above do for a clip of that length (the reference takes one video of any length per
+ * call, extract_features.py:80-97): an empty clip gives SASVQA_STATUS_EMPTY and zero frames, W == -1 is T_b / 20 per
+ * clip, the fallback with T_b < K gives SASVQA_STATUS_TOO_FEW.  lcl_avg / feats are packed per frame ([sum T],
+ * [sum T, 768]); idx [B, K], status [B], sampled [B, K, 3*224*224]. */
+int sasvqa_mdf_sample_ragged_u8(SasvqaEncoder* enc, const uint8_t* frames_hwc_dev, int B, const int32_t* clip_offsets_host,
+                                int H, int W, int K, int Wwin, int32_t* idx_dev, int32_t* status_dev,
+                                float* lcl_avg_or_null_dev, float* feats_or_null_dev, float* sampled_or_null_dev,
+                                void* stream);
+
 /* ---- whole path, HOST buffers (the extraction loop extract_features.py:80-97 for a clip list) --
  * Streams clips host->device in double-buffered groups overlapped with compute, writes idx/status
  * (and, if not NULL, the sampled frames -- the rows of the reference's "sampled_frames" dataset)

@@ -21,6 +21,8 @@ int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, c
 int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int, int, int32_t*, int32_t*,
                       float*, float*, float*, cudaStream_t);
 int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int, int, int32_t*, int32_t*, float*);
+int mdf_sample_ragged_device(SasvqaEncoder*, const uint8_t*, const float*, int, const int32_t*, int, int, int, int, int32_t*,
+                             int32_t*, float*, float*, float*, cudaStream_t);
 int encoder_set_projection(SasvqaEncoder*, const float*, const float*, const float*, const float*);
 int visual_tokens(SasvqaEncoder*, const uint8_t*, const float*, int, int, float*, cudaStream_t);
 int mif_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, const float*, int, int, int32_t*,
@@ -140,6 +142,12 @@ int sasvqa_mdf_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips, int B, int
                             int32_t* status, float* lcl_avg, float* feats, float* sampled, void* stream) {
     SASVQA_REQUIRE(B == 0 || T == 0 || clips != nullptr, "null clips");
     return mdf_sample_device(enc, clips, nullptr, B, T, H, Wd, K, W, idx, status, lcl_avg, feats, sampled, S(stream));
+}
+int sasvqa_mdf_sample_ragged_u8(SasvqaEncoder* enc, const uint8_t* frames, int B, const int32_t* clip_offsets_host, int H,
+                                int Wd, int K, int W, int32_t* idx, int32_t* status, float* lcl_avg, float* feats,
+                                float* sampled, void* stream) {
+    return mdf_sample_ragged_device(enc, frames, nullptr, B, clip_offsets_host, H, Wd, K, W, idx, status, lcl_avg, feats, sampled,
+                                    S(stream));
 }
 int sasvqa_resize_crop_u8(const uint8_t* frames, int n_frames, int H, int Wd, uint8_t* out, void* stream) {
     return launch_resize_crop_u8(frames, n_frames, H, Wd, nullptr, 0, n_frames, out, S(stream));

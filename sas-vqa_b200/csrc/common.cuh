@@ -110,15 +110,19 @@ int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, CUtensorMap* ma
                         uint64_t rows);
 int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, const CUtensorMap* map_out,
                              __nv_bfloat16* out, int n_frames, int num_sms, cudaStream_t s, int variant = 0);
-int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s);
+// clip_off (device, [B + 1]) switches the selection stages to RAGGED batches: clip b = rows [clip_off[b], clip_off[b+1]) of the
+// packed per-frame arrays, T = the longest clip, W may be -1 (adaptive per clip)
+int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s,
+                      const int32_t* clip_off = nullptr);
 int launch_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status,
-                      cudaStream_t s);
+                      cudaStream_t s, const int32_t* clip_off = nullptr);
 int launch_mif_scores(const float* feats, const float* q, int B, int T, float* scores, cudaStream_t s);
 int launch_topk_strided(const float* scores, int B, int T, int ds_rate, int K, int32_t* idx,
-                        const int32_t* only_if_status, cudaStream_t s);
-int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s);
+                        const int32_t* only_if_status, cudaStream_t s, const int32_t* clip_off = nullptr);
+int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s,
+                     const int32_t* clip_off = nullptr);
 int launch_gather_f32(const float* frames, const int32_t* idx, int B, int T, int K, int64_t row_elems, float* out,
-                      cudaStream_t s);
+                      cudaStream_t s, const int32_t* clip_off = nullptr);
 
 // MIF cross-encoder (BERT sequence classifier, src/preprocessing/gen_sample.py:79-83): packed variable-length rows
 int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens_dev, int row_base,

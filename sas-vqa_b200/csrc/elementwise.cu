@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(POOL_WARPS * 32) pool_norm_kernel(const float*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gather_u8_kernel(const uint8_t* __restrict__ clips,
                                                          const int32_t* __restrict__ idx, int B, int T, int K,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, const int32_t* __restrict__ clip_off) {
     __shared__ float lut[3][256];                                // exact normalised value of every possible input
     for (int i = threadIdx.x; i < 768; i += blockDim.x) {
         const int c = i >> 8;
@@ -292,10 +292,12 @@ __global__ void __launch_bounds__(256) gather_u8_kernel(const uint8_t* __restric
         const long long bk = r / kImg;
         const long long b = bk / K;
         const int t = idx[bk];
-        const bool ok = t >= 0 && t < T;
+        const long long f0 = clip_off ? (long long)clip_off[b] : b * T;            // ragged batch: the clip's own span
+        const int Tb = clip_off ? clip_off[b + 1] - clip_off[b] : T;
+        const bool ok = t >= 0 && t < Tb;
         uint32_t w[12] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
         if (ok) {
-            const uint4* src = reinterpret_cast<const uint4*>(clips + (((b * T + t) * kImg + y) * kImg + xc * 16) * 3);
+            const uint4* src = reinterpret_cast<const uint4*>(clips + (((f0 + t) * kImg + y) * kImg + xc * 16) * 3);
             const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
             w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
             w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
@@ -322,14 +324,17 @@ __global__ void __launch_bounds__(256) gather_u8_kernel(const uint8_t* __restric
 
 __global__ void __launch_bounds__(256) gather_f32_kernel(const float4* __restrict__ frames,
                                                           const int32_t* __restrict__ idx, int B, int T, int K,
-                                                          long long row_vec4, float4* __restrict__ out) {
+                                                          long long row_vec4, float4* __restrict__ out,
+                                                          const int32_t* __restrict__ clip_off) {
     const long long total = (long long)B * K * row_vec4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long bk = i / row_vec4, e = i - bk * row_vec4;
         const long long b = bk / K;
         const int t = idx[bk];
-        out[i] = (t >= 0 && t < T) ? __ldg(frames + (b * T + t) * row_vec4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long f0 = clip_off ? (long long)clip_off[b] : b * T;
+        const int Tb = clip_off ? clip_off[b + 1] - clip_off[b] : T;
+        out[i] = (t >= 0 && t < Tb) ? __ldg(frames + (f0 + t) * row_vec4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -528,24 +533,25 @@ int launch_pool_norm(const float* x, int n_frames, const float* gamma, const flo
     return 0;
 }
 
-int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s) {
+int launch_gather_u8(const uint8_t* clips, const int32_t* idx, int B, int T, int K, float* out, cudaStream_t s,
+                     const int32_t* clip_off) {
     if (B == 0 || K == 0) return 0;
     SASVQA_REQUIRE(((uintptr_t)clips & 15) == 0 && ((uintptr_t)out & 31) == 0, "unaligned buffers");
     const long long total = (long long)B * K * kImg * (kImg / 16);
-    gather_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(clips, idx, B, T, K, out);
+    gather_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(clips, idx, B, T, K, out, clip_off);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;
 }
 
 int launch_gather_f32(const float* frames, const int32_t* idx, int B, int T, int K, int64_t row_elems, float* out,
-                      cudaStream_t s) {
+                      cudaStream_t s, const int32_t* clip_off) {
     if (B == 0 || K == 0 || row_elems == 0) return 0;
     SASVQA_REQUIRE(row_elems % 4 == 0, "row_elems must be a multiple of 4");
     SASVQA_REQUIRE(((uintptr_t)frames & 15) == 0 && ((uintptr_t)out & 15) == 0, "unaligned buffers");
     const long long total = (long long)B * K * (row_elems / 4);
     gather_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(frames), idx, B, T, K,
-                                                           row_elems / 4, reinterpret_cast<float4*>(out));
+                                                           row_elems / 4, reinterpret_cast<float4*>(out), clip_off);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -31,12 +31,14 @@ __global__ void fill_i32_kernel(int32_t* p, int32_t v, int n) {
     if (i < n) p[i] = v;
 }
 // selected (clip, index) pairs -> flat source frame numbers for the resize-on-gather path; picks < 0 stay < 0
-__global__ void frame_map_kernel(const int32_t* idx, int B, int T, int K, int32_t* map, int32_t* unit_idx) {
+__global__ void frame_map_kernel(const int32_t* idx, int B, int T, int K, int32_t* map, int32_t* unit_idx,
+                                 const int32_t* clip_off) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * K) return;
-    const int t = idx[i];
-    const bool ok = t >= 0 && t < T;
-    map[i] = ok ? (i / K) * T + t : -1;
+    const int t = idx[i], b = i / K;
+    const int f0 = clip_off ? clip_off[b] : b * T, Tb = clip_off ? clip_off[b + 1] - clip_off[b] : T;
+    const bool ok = t >= 0 && t < Tb;
+    map[i] = ok ? f0 + t : -1;
     unit_idx[i] = ok ? 0 : -1;
 }
 
@@ -98,6 +100,8 @@ struct SasvqaEncoder {
     size_t picked_cap = 0;
     int32_t* pick_map = nullptr;
     size_t pick_map_cap = 0;
+    int32_t* clip_off = nullptr;          // ragged batches: [B + 1] frame offsets of the clips
+    size_t clip_off_cap = 0;
     // host-buffer pipeline
     cudaStream_t h2d_stream = nullptr, compute_stream = nullptr, d2h_stream = nullptr;
     uint8_t* stage[2] = {nullptr, nullptr};
@@ -386,7 +390,7 @@ void encoder_destroy(SasvqaEncoder* e) {
     cudaFree(e->x); cudaFree(e->h); cudaFree(e->big);
     cudaFree(e->w_proj); cudaFree(e->proj_vec);
     cudaFree(e->feats); cudaFree(e->lcl);
-    cudaFree(e->resized); cudaFree(e->picked); cudaFree(e->pick_map);
+    cudaFree(e->resized); cudaFree(e->picked); cudaFree(e->pick_map); cudaFree(e->clip_off);
     for (int i = 0; i < 2; ++i) {
         cudaFree(e->stage[i]); cudaFree(e->out_stage[i]); cudaFree(e->idx_stage[i]);
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
@@ -542,9 +546,10 @@ int visual_tokens(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int n_f
 
 // K5 for any frame size: the sampled rows are the image processor's output for the K picks of every clip
 static int gather_picks(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int H, int Wd, int K,
-                        const int32_t* idx, float* sampled, cudaStream_t s) {
+                        const int32_t* idx, float* sampled, cudaStream_t s, const int32_t* clip_off = nullptr,
+                        long long n_frames_total = -1) {
     int rc = 0;
-    const size_t nf = (size_t)B * T;
+    const size_t nf = n_frames_total >= 0 ? (size_t)n_frames_total : (size_t)B * T;
     if (u8 && (H != kImg || Wd != kImg)) {                       // resize only the picks, then gather
         const size_t np = (size_t)B * K;
         if ((rc = grow((void**)&e->picked, &e->picked_cap, np * kFrameElems))) return rc;
@@ -552,7 +557,7 @@ static int gather_picks(SasvqaEncoder* e, const uint8_t* u8, const float* f32, i
         int32_t* unit_idx = e->pick_map + np;
         {
             Scope sc(e, PK_RESIZE, s);
-            frame_map_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(idx, B, T, K, e->pick_map, unit_idx);
+            frame_map_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(idx, B, T, K, e->pick_map, unit_idx, clip_off);
             SASVQA_CUDA_CHECK(cudaGetLastError());
             count_launch();
             if ((rc = launch_resize_crop_u8(u8, (long long)nf, H, Wd, e->pick_map, 0, (int)np, e->picked, s))) return rc;
@@ -561,9 +566,64 @@ static int gather_picks(SasvqaEncoder* e, const uint8_t* u8, const float* f32, i
         return launch_gather_u8(e->picked, unit_idx, (int)np, 1, 1, sampled, s);
     }
     Scope sc(e, PK_GATHER, s);
-    if (u8) rc = launch_gather_u8(u8, idx, B, T, K, sampled, s);
-    else rc = launch_gather_f32(f32, idx, B, T, K, kFrameElems, sampled, s);
+    if (u8) rc = launch_gather_u8(u8, idx, B, T, K, sampled, s, clip_off);
+    else rc = launch_gather_f32(f32, idx, B, T, K, kFrameElems, sampled, s, clip_off);
     return rc;
+}
+
+// Ragged batch: B clips of different lengths packed back to back, clip b = frames [off[b], off[b+1]) (the reference
+// handles one video of any length per call, extract_features.py:80-97; real datasets are ragged).  The encoder is
+// frame-batched already; the selection stages take the offsets.  Per clip exactly what the uniform path does for a
+// clip of that length: T_b == 0 -> status EMPTY, zero frames; W == -1 -> T_b / 20; T_b < K on the fallback -> TOO_FEW.
+// lcl_out / feats_out are packed per frame ([sum T], [sum T, 768]).
+int mdf_sample_ragged_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, const int32_t* off_host, int H,
+                             int Wd, int K, int W, int32_t* idx, int32_t* status, float* lcl_out, float* feats_out,
+                             float* sampled, cudaStream_t s) {
+    SASVQA_REQUIRE(e != nullptr && idx != nullptr && status != nullptr && off_host != nullptr, "null argument");
+    SASVQA_REQUIRE(B >= 0 && K >= 1 && K <= 2048, "bad B/K");
+    SASVQA_REQUIRE(H > 0 && Wd > 0, "bad frame size");
+    SASVQA_REQUIRE(u8 != nullptr || f32 != nullptr || off_host[B] == 0, "null frames");
+    SASVQA_REQUIRE(u8 != nullptr || (H == kImg && Wd == kImg), "fp32 frames are already processed: they must be 224x224");
+    SASVQA_REQUIRE(W >= -1, "W must be >= 0, or -1 for the adaptive width T / 20");
+    if (B == 0) return 0;
+    SASVQA_REQUIRE(off_host[0] == 0, "clip offsets must start at 0");
+    int t_max = 0;
+    for (int b = 0; b < B; ++b) {
+        SASVQA_REQUIRE(off_host[b + 1] >= off_host[b], "clip offsets must not decrease");
+        t_max = std::max(t_max, off_host[b + 1] - off_host[b]);
+    }
+    const long long nf = off_host[B];
+    int rc;
+    if ((rc = grow((void**)&e->clip_off, &e->clip_off_cap, ((size_t)B + 1) * sizeof(int32_t)))) return rc;
+    SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->clip_off, off_host, ((size_t)B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (t_max == 0) {                                           // every clip empty
+        fill_i32_kernel<<<(B + 255) / 256, 256, 0, s>>>(status, SASVQA_STATUS_EMPTY, B);
+        fill_i32_kernel<<<(B * K + 255) / 256, 256, 0, s>>>(idx, -1, B * K);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        if (sampled) SASVQA_CUDA_CHECK(cudaMemsetAsync(sampled, 0, (size_t)B * K * kFrameElems * sizeof(float), s));
+        return 0;
+    }
+    float* feats = feats_out;
+    if (!feats) {
+        if ((rc = grow((void**)&e->feats, &e->feats_cap, (size_t)nf * kHidden * sizeof(float)))) return rc;
+        feats = e->feats;
+    }
+    float* lcl = lcl_out;
+    if (!lcl) {
+        if ((rc = grow((void**)&e->lcl, &e->lcl_cap, (size_t)nf * sizeof(float)))) return rc;
+        lcl = e->lcl;
+    }
+    if ((rc = encode_frames(e, u8, f32, nf, H, Wd, feats, s))) return rc;
+    {
+        Scope sc(e, PK_SCORES, s);
+        if ((rc = launch_mdf_scores(feats, B, t_max, W, lcl, nullptr, s, e->clip_off))) return rc;
+    }
+    {
+        Scope sc(e, PK_SELECT, s);
+        if ((rc = launch_mdf_select(lcl, B, t_max, K, W, idx, status, s, e->clip_off))) return rc;
+    }
+    if (sampled && (rc = gather_picks(e, u8, f32, B, t_max, H, Wd, K, idx, sampled, s, e->clip_off, nf))) return rc;
+    return 0;
 }
 
 int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int B, int T, int H, int Wd, int K, int W,

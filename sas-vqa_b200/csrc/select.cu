@@ -30,14 +30,22 @@ namespace {
 constexpr int SC_SEG = 32;
 constexpr int SC_THREADS = kHidden / 4;      // 192
 
+// Ragged batches (clip_off != nullptr): clip b owns frames [clip_off[b], clip_off[b+1]) of the packed feature matrix,
+// T is then the longest clip (it sizes the grid) and W == -1 selects the adaptive width T_b / 20 per clip (utils.py:32-33).
 __global__ void __launch_bounds__(SC_THREADS) mdf_scores_kernel(const float* __restrict__ feats, int T, int W, int n_seg,
-                                                                 float* __restrict__ lcl) {
+                                                                 float* __restrict__ lcl, const int32_t* __restrict__ clip_off) {
     __shared__ float red[SC_SEG][SC_THREADS + 1];
     const long long b = blockIdx.x / n_seg;
     const int seg = blockIdx.x - (int)b * n_seg;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    long long row0 = b * T;
+    if (clip_off != nullptr) {
+        row0 = clip_off[b];
+        T = clip_off[b + 1] - clip_off[b];
+    }
+    if (W < 0) W = T / 20;
     const int lo = W, hi = T - W;                       // frames with a full window: [lo, hi)
-    float* out = lcl + b * T;
+    float* out = lcl + row0;
     if (seg == 0) {                                      // borders stay exactly 0.0 (utils.py:57)
         for (int i = t; i < T; i += SC_THREADS)
             if (i < lo || i >= hi) out[i] = 0.0f;
@@ -45,7 +53,7 @@ __global__ void __launch_bounds__(SC_THREADS) mdf_scores_kernel(const float* __r
     const int i0 = lo + seg * SC_SEG;
     if (i0 >= hi) return;
     const int n = min(SC_SEG, hi - i0);
-    const float4* rows = reinterpret_cast<const float4*>(feats + b * T * (long long)kHidden) + t;    // + i * 192 per row
+    const float4* rows = reinterpret_cast<const float4*>(feats + row0 * (long long)kHidden) + t;     // + i * 192 per row
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int j = i0 - W; j < i0 + W; ++j) {
         const float4 v = __ldg(rows + (long long)j * SC_THREADS);
@@ -163,7 +171,8 @@ __device__ __forceinline__ int warp_first_argmax(const float* __restrict__ v, in
 // 3 = T < K (the reference's fallback raises).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) mdf_greedy_kernel(const float* __restrict__ lcl_all, int T, int K, int W,
-                                                         int32_t* __restrict__ idx_all, int32_t* __restrict__ status) {
+                                                         int32_t* __restrict__ idx_all, int32_t* __restrict__ status,
+                                                         const int32_t* __restrict__ clip_off) {
     extern __shared__ int32_t sel_smem[];
     float* iv_score = reinterpret_cast<float*>(sel_smem);
     int32_t* iv_l = sel_smem + (K + 2);
@@ -171,8 +180,19 @@ __global__ void __launch_bounds__(32) mdf_greedy_kernel(const float* __restrict_
     int32_t* iv_p = sel_smem + 3 * (K + 2);
     const int lane = threadIdx.x;
     const long long b = blockIdx.x;
-    const float* lcl = lcl_all + b * T;
+    long long row0 = b * T;
+    if (clip_off != nullptr) {                                  // ragged batch: this clip's own length (and window)
+        row0 = clip_off[b];
+        T = clip_off[b + 1] - clip_off[b];
+    }
+    if (W < 0) W = T / 20;
+    const float* lcl = lcl_all + row0;
     int32_t* out = idx_all + b * K;
+    if (T == 0) {                                               // utils.py:50-52: empty clip, 'Zeros'
+        for (int k = lane; k < K; k += 32) out[k] = -1;
+        if (lane == 0) status[b] = 2;
+        return;
+    }
 
     int n_open = 0;
     auto push = [&](int l, int r) {
@@ -252,12 +272,18 @@ __device__ __forceinline__ uint64_t topk_key(float x, uint32_t pos) {
 // one CTA per row; n = ceil(T / stride) <= n_pad (power of two) keys bitonic-sorted in shared memory
 __global__ void __launch_bounds__(256) topk_bitonic_kernel(const float* __restrict__ scores, int T, int stride, int K,
                                                             int n_pad, int32_t* __restrict__ idx_all,
-                                                            const int32_t* __restrict__ only_if_status) {
+                                                            const int32_t* __restrict__ only_if_status,
+                                                            const int32_t* __restrict__ clip_off) {
     extern __shared__ uint64_t keys[];
     const long long b = blockIdx.x;
     if (only_if_status != nullptr && only_if_status[b] != 1) return;
+    long long row0 = b * T;
+    if (clip_off != nullptr) {
+        row0 = clip_off[b];
+        T = clip_off[b + 1] - clip_off[b];
+    }
     const int n = (T + stride - 1) / stride;
-    const float* v = scores + b * T;
+    const float* v = scores + row0;
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
         keys[i] = i < n ? topk_key(v[(long long)i * stride], (uint32_t)i) : ~0ull;
     __syncthreads();
@@ -284,13 +310,19 @@ __global__ void __launch_bounds__(256) topk_bitonic_kernel(const float* __restri
 // any T: K rounds of a block-wide "smallest key greater than the previous pick"
 __global__ void __launch_bounds__(256) topk_rounds_kernel(const float* __restrict__ scores, int T, int stride, int K,
                                                            int32_t* __restrict__ idx_all,
-                                                           const int32_t* __restrict__ only_if_status) {
+                                                           const int32_t* __restrict__ only_if_status,
+                                                           const int32_t* __restrict__ clip_off) {
     __shared__ uint64_t red[8];
     __shared__ uint64_t prev_s;
     const long long b = blockIdx.x;
     if (only_if_status != nullptr && only_if_status[b] != 1) return;
+    long long row0 = b * T;
+    if (clip_off != nullptr) {
+        row0 = clip_off[b];
+        T = clip_off[b + 1] - clip_off[b];
+    }
     const int n = (T + stride - 1) / stride;
-    const float* v = scores + b * T;
+    const float* v = scores + row0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t prev = 0;
     bool have_prev = false;
@@ -322,14 +354,16 @@ __global__ void __launch_bounds__(256) topk_rounds_kernel(const float* __restric
 
 }  // namespace
 
-int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s) {
+int launch_mdf_scores(const float* feats, int B, int T, int W, float* lcl_avg, float* gram, cudaStream_t s,
+                      const int32_t* clip_off) {
     if (B == 0 || T == 0) return 0;
-    SASVQA_REQUIRE(W >= 0, "W must be >= 0 here (resolve W = -1 to T / 20 on the host)");
+    SASVQA_REQUIRE(W >= 0 || clip_off != nullptr, "W must be >= 0 here (resolve W = -1 to T / 20 on the host)");
+    SASVQA_REQUIRE(clip_off == nullptr || gram == nullptr, "the full Gram output is for uniform batches");
     SASVQA_REQUIRE(((uintptr_t)feats & 15) == 0, "feats must be 16-byte aligned");
-    const int n_seg = std::max(1, (T - 2 * W + SC_SEG - 1) / SC_SEG);
+    const int n_seg = std::max(1, (T - 2 * std::max(W, 0) + SC_SEG - 1) / SC_SEG);
     const long long blocks = (long long)B * n_seg;
     SASVQA_REQUIRE(blocks < 2147483647LL, "too many frames for one scores launch");
-    mdf_scores_kernel<<<(unsigned)blocks, SC_THREADS, 0, s>>>(feats, T, W, n_seg, lcl_avg);
+    mdf_scores_kernel<<<(unsigned)blocks, SC_THREADS, 0, s>>>(feats, T, W, n_seg, lcl_avg, clip_off);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     if (gram != nullptr) {
@@ -354,17 +388,17 @@ int launch_mif_scores(const float* feats, const float* q, int B, int T, float* s
 }
 
 int launch_topk_strided(const float* scores, int B, int T, int ds_rate, int K, int32_t* idx,
-                        const int32_t* only_if_status, cudaStream_t s) {
+                        const int32_t* only_if_status, cudaStream_t s, const int32_t* clip_off) {
     if (B == 0 || K == 0) return 0;
     SASVQA_REQUIRE(ds_rate >= 1, "ds_rate must be >= 1");
-    const int n = (T + ds_rate - 1) / ds_rate;
+    const int n = (T + ds_rate - 1) / ds_rate;                  // ragged: T is the longest clip, rows are filtered by status
     SASVQA_REQUIRE(K <= n, "selected index k out of range");
     int n_pad = 1;
     while (n_pad < n) n_pad <<= 1;
     if (n_pad <= 4096) {
-        topk_bitonic_kernel<<<B, 256, n_pad * sizeof(uint64_t), s>>>(scores, T, ds_rate, K, n_pad, idx, only_if_status);
+        topk_bitonic_kernel<<<B, 256, n_pad * sizeof(uint64_t), s>>>(scores, T, ds_rate, K, n_pad, idx, only_if_status, clip_off);
     } else {
-        topk_rounds_kernel<<<B, 256, 0, s>>>(scores, T, ds_rate, K, idx, only_if_status);
+        topk_rounds_kernel<<<B, 256, 0, s>>>(scores, T, ds_rate, K, idx, only_if_status, clip_off);
     }
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -372,16 +406,16 @@ int launch_topk_strided(const float* scores, int B, int T, int ds_rate, int K, i
 }
 
 int launch_mdf_select(const float* lcl_avg, int B, int T, int K, int W, int32_t* idx, int32_t* status,
-                      cudaStream_t s) {
+                      cudaStream_t s, const int32_t* clip_off) {
     if (B == 0) return 0;
-    SASVQA_REQUIRE(T >= 1 && K >= 1 && W >= 0, "mdf_select needs T >= 1, K >= 1, W >= 0");
+    SASVQA_REQUIRE(T >= 1 && K >= 1 && (W >= 0 || clip_off != nullptr), "mdf_select needs T >= 1, K >= 1, W >= 0");
     SASVQA_REQUIRE(K <= 2048, "K too large");
     const size_t smem = 4 * (size_t)(K + 2) * sizeof(int32_t);
-    mdf_greedy_kernel<<<B, 32, smem, s>>>(lcl_avg, T, K, W, idx, status);
+    mdf_greedy_kernel<<<B, 32, smem, s>>>(lcl_avg, T, K, W, idx, status, clip_off);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     if (T >= K) {   // fallback rows (status == 1): discard the greedy picks, plain top-K (utils.py:91-93)
-        int rc = launch_topk_strided(lcl_avg, B, T, 1, K, idx, status, s);
+        int rc = launch_topk_strided(lcl_avg, B, T, 1, K, idx, status, s, clip_off);
         if (rc) return rc;
     }
     return 0;

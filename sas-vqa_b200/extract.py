@@ -3,9 +3,10 @@ over already decoded clips (cv2 decoding is outside the hot path, SURVEY.md 8(a)
 ``sampled_frames`` dataset (+ optional index table) out.
 
 The reference handles one video per iteration -- queue get, sampler call, ``.cpu()``, H5 row write, all serial
-(``:80-97``).  Here clips of equal shape are grouped, every group goes through the host-buffer C-ABI call
-(H2D, encoder and D2H of consecutive groups overlapped on three streams), and the K frames of every clip land
-directly in that clip's row of the dataset.
+(``:80-97``).  Here consecutive clips of one frame size are one batch: equal lengths go through the host-buffer C-ABI
+call (H2D, encoder and D2H of consecutive groups overlapped on three streams), different lengths through the ragged
+device call (one frame-batched encoder pass, selection kernels on per-clip offsets), and the K frames of every clip
+land directly in that clip's row of the dataset.
 """
 from __future__ import annotations
 
@@ -33,23 +34,33 @@ def generate_h5(clips, model, K: int, W: int, h5_outfile: str, sampling_strategy
     all_idx = np.full((n, K), -1, dtype=np.int64)
     with writer.SampledFramesWriter(h5_outfile, n, K) as out:
         if sampling_strategy == "repr":
-            # group consecutive clips of identical shape so that one C-ABI call pipelines them
+            # consecutive clips of one frame size are one batch whatever their lengths: equal lengths take the
+            # host-buffer call (copies overlapped with compute), different lengths the ragged device call
             i = 0
             while i < n:
                 j = i + 1
-                while j < n and j - i < group_clips and tuple(clips[j].shape) == tuple(clips[i].shape):
+                while j < n and j - i < group_clips and tuple(clips[j].shape[1:]) == tuple(clips[i].shape[1:]):
                     j += 1
-                batch = torch.stack([torch.as_tensor(c) for c in clips[i:j]])
-                if batch.shape[1] == 0:                                             # utils.py:50-52
+                group = [torch.as_tensor(c) for c in clips[i:j]]
+                uniform = all(c.shape[0] == group[0].shape[0] for c in group)
+                if uniform and group[0].shape[0] == 0:                              # utils.py:50-52
                     dc["Zeros"] += j - i
                     out[i:j] = np.zeros((j - i, K, 3 * 224 * 224), dtype=np.float32)
                 else:
-                    host = batch.pin_memory() if torch.cuda.is_available() else batch
-                    res = ops.mdf_sample_host(enc, host, K, W)
+                    if uniform:
+                        batch = torch.stack(group)
+                        host = batch.pin_memory() if torch.cuda.is_available() else batch
+                        res = ops.mdf_sample_host(enc, host, K, W)
+                    else:
+                        if not torch.cuda.is_available():
+                            raise ops._capi.SasvqaError("generate_h5 needs a CUDA device (no CPU fallback)")
+                        res = sampler.sample_mdf_ragged(group, enc, K, W)
+                        res = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in res.items()}
                     st = res["status"]
                     if bool((st == ops.STATUS_TOO_FEW).any()):                       # utils.py:92: topk raises
                         raise RuntimeError("selected index k out of range")
                     dc["Failure"] += int((st == ops.STATUS_FALLBACK).sum())
+                    dc["Zeros"] += int((st == ops.STATUS_EMPTY).sum())
                     out[i:j] = res["frames"].reshape(j - i, K, -1)
                     all_idx[i:j] = res["indices"].numpy()
                 i = j

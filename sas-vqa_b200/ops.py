@@ -311,6 +311,34 @@ def mdf_sample_device(enc: FrameEncoder, clips: torch.Tensor, K: int, W: int, wa
     return dict(indices=idx, status=status, lcl_avg=lcl, feats=feats, frames=sampled)
 
 
+def mdf_sample_ragged(enc: FrameEncoder, frames: torch.Tensor, lengths, K: int, W: int, want_frames: bool = True,
+                      want_aux: bool = False) -> dict:
+    """Ragged batch: ``frames`` [sum(lengths), H, W, 3] uint8 on the GPU, clip b = the next ``lengths[b]`` frames.
+    Returns dict(indices int32 [B, K], status [B], frames [B, K, 3, 224, 224] | None, lcl_avg [sum T], feats [sum T, 768],
+    offsets int32 [B + 1] on the CPU)."""
+    frames = _need_cuda(frames, torch.uint8, "frames")
+    if frames.dim() != 4 or frames.shape[-1] != 3:
+        raise ValueError(f"frames must be [sum T, H, W, 3], got {tuple(frames.shape)}")
+    lens = torch.as_tensor(lengths, dtype=torch.int64).reshape(-1)
+    if int(lens.sum()) != int(frames.shape[0]) or bool((lens < 0).any()):
+        raise ValueError(f"lengths sum to {int(lens.sum())}, frames holds {int(frames.shape[0])}")
+    B = int(lens.numel())
+    off = torch.zeros(B + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(lens, 0).to(torch.int32)
+    nf, H, Wd = (int(v) for v in frames.shape[:3])
+    dev = frames.device
+    idx = torch.empty(B, K, dtype=torch.int32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    lcl = torch.empty(nf, dtype=torch.float32, device=dev) if want_aux else None
+    feats = torch.empty(nf, HIDDEN, dtype=torch.float32, device=dev) if want_aux else None
+    sampled = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, device=dev) if want_frames else None
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().sasvqa_mdf_sample_ragged_u8(
+            enc.handle, frames.data_ptr(), B, off.data_ptr(), H, Wd, int(K), int(W), idx.data_ptr(), status.data_ptr(),
+            _capi.ptr(lcl), _capi.ptr(feats), _capi.ptr(sampled), _stream(frames)), "sasvqa_mdf_sample_ragged_u8")
+    return dict(indices=idx, status=status, lcl_avg=lcl, feats=feats, frames=sampled, offsets=off)
+
+
 def mdf_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, K: int, W: int, idx_out: torch.Tensor = None,
                     status_out: torch.Tensor = None, frames_out: torch.Tensor = None, want_frames: bool = True) -> dict:
     """clips_host: [B, T, H, W, 3] uint8 in (ideally pinned) host memory.  Results land in host tensors."""

@@ -78,6 +78,31 @@ def sample_mdf_batch(clips: torch.Tensor, model, K: int = 16, W: int = 8, debug_
     return res
 
 
+def sample_mdf_ragged(clips, model, K: int = 16, W: int = 8, debug_counter=None, want_frames: bool = True,
+                      want_aux: bool = False) -> dict:
+    """Batched MDF over clips of DIFFERENT lengths (one frame size): ``clips`` is a sequence of uint8 tensors
+    [T_i, H, W, 3] (CPU or GPU; concatenated and moved to the GPU here).  One library call for the whole batch -- the
+    encoder is frame-batched, the selection kernels take per-clip offsets -- with per clip exactly the result of the
+    reference's one-video-per-call loop (extract_features.py:80-97): empty clips give zero frames ('Zeros'), W == -1
+    adapts per clip, the fallback counts a 'Failure'.  Returns the dict of ``sample_mdf_batch`` with per-frame
+    ``lcl_avg`` / ``feats`` packed, plus ``offsets``."""
+    enc = as_frame_encoder(model)
+    clips = [torch.as_tensor(c) for c in clips]
+    lengths = [int(c.shape[0]) for c in clips]
+    if not clips:
+        raise ValueError("empty clip list")
+    shapes = {tuple(c.shape[1:]) for c in clips}
+    if len(shapes) != 1:
+        raise ValueError(f"all clips of a ragged batch must share one frame size, got {sorted(shapes)}")
+    frames = torch.cat([c.to(enc.device) for c in clips], dim=0)
+    res = ops.mdf_sample_ragged(enc, frames, lengths, K, W, want_frames=want_frames, want_aux=want_aux)
+    if debug_counter is not None:
+        st = res["status"].cpu()
+        debug_counter["Failure"] += int((st == ops.STATUS_FALLBACK).sum())
+        debug_counter["Zeros"] += int((st == ops.STATUS_EMPTY).sum())
+    return res
+
+
 def sample_mdf_host(clips_host: torch.Tensor, model, K: int = 16, W: int = 8, debug_counter=None, **kw) -> dict:
     """Same for clips in host memory ([B, T, 224, 224, 3] uint8, pinned for full speed): the
     extraction loop extract_features.py:80-97 over a clip list, copies overlapped with compute."""

@@ -493,7 +493,8 @@ def test_generate_h5_rows_match_reference_style_loop(encoder, tmp_path):
     from sasvqa_b200 import writer
     K, W = 4, 2
     clips = [synth.make_clip(80, 24), synth.make_clip(81, 24), synth.make_clip(82, 20, H=240, W=320),
-             torch.zeros(0, 224, 224, 3, dtype=torch.uint8), synth.make_clip(83, 24)]
+             torch.zeros(0, 224, 224, 3, dtype=torch.uint8), synth.make_clip(83, 24), synth.make_clip(84, 31),
+             synth.make_clip(85, 12, H=240, W=320), synth.make_clip(86, 19, H=240, W=320)]     # ragged groups of both sizes
     path = str(tmp_path / "msvd_qa_video_feat.h5")
     res = sas.generate_h5(clips, encoder, K, W, path, inds_outfile=str(tmp_path / "mdf_inds.json"))
     ds = writer.open_sampled_frames(path)
@@ -518,6 +519,47 @@ def test_generate_h5_rows_match_reference_style_loop(encoder, tmp_path):
             want = sas.sample_frames_uniform(frames, K) if strategy == "uni" else \
                 sas.sample_frame_indices(frames, K, 4, len(frames))
             assert np.array_equal(np.asarray(ds2[i]), want.reshape(K, -1).numpy()), (strategy, i)
+
+
+@pytest.mark.parametrize("W", [3, -1], ids=["W3", "adaptive"])
+def test_ragged_batch_equals_one_call_per_clip(encoder, W):
+    """Clips of different lengths in ONE library call == the reference's one-video-per-call loop
+    (extract_features.py:80-97), bit for bit: an empty clip, T < K (fallback raises there: TOO_FEW), T <= 2W (all-zero
+    scores), a fallback clip, long clips; per-clip adaptive window with W = -1."""
+    K = 6
+    lengths = [40, 0, 17, 64, 5, 23, 128, 9, 6]
+    clips = [synth.make_clip(300 + i, T) for i, T in enumerate(lengths)]
+    dc = {"Failure": 0, "Zeros": 0}
+    res = sas.sample_mdf_ragged(clips, encoder, K, W, debug_counter=dc, want_aux=True)
+    assert res["offsets"].tolist() == [0] + list(np.cumsum(lengths))
+    n_fail = 0
+    for b, (clip, T) in enumerate(zip(clips, lengths)):
+        lo, hi = int(res["offsets"][b]), int(res["offsets"][b + 1])
+        if T == 0:
+            assert int(res["status"][b]) == ops.STATUS_EMPTY and res["indices"][b].cpu().tolist() == [-1] * K
+            assert float(res["frames"][b].abs().sum()) == 0.0
+            continue
+        one = sas.sample_mdf_batch(clip.unsqueeze(0).to(DEV), encoder, K, W, want_aux=True)
+        assert int(res["status"][b]) == int(one["status"][0]), (b, T)
+        assert torch.equal(res["feats"][lo:hi], one["feats"][0]) and torch.equal(res["lcl_avg"][lo:hi], one["lcl_avg"][0])
+        if int(one["status"][0]) != ops.STATUS_TOO_FEW:
+            assert torch.equal(res["indices"][b], one["indices"][0]), (b, T)
+            assert torch.equal(res["frames"][b], one["frames"][0])
+        n_fail += int(one["status"][0]) == ops.STATUS_FALLBACK
+    assert dc == {"Failure": n_fail, "Zeros": 1}
+    if W == 3:                              # T = 5 < K = 6 on the fallback path: the reference's topk raises
+        assert int(res["status"][4]) == ops.STATUS_TOO_FEW
+    else:                                   # T // 20 = 0 for the short clips: a zero-width window re-offers the first
+        assert int(res["status"][4]) == ops.STATUS_OK      # maximum for ever (utils.py:67-88), K picks of one frame
+        assert len(set(res["indices"][4].cpu().tolist())) == 1
+    # decoded frames of another size: K0 on the chunks and on the picks, offsets carried through the pick map
+    small = [synth.make_clip(320 + i, T, H=120, W=160) for i, T in enumerate((14, 33, 8))]
+    rs = sas.sample_mdf_ragged(small, encoder, 4, 2)
+    for b, clip in enumerate(small):
+        one = sas.sample_mdf_batch(clip.unsqueeze(0).to(DEV), encoder, 4, 2)
+        assert torch.equal(rs["indices"][b], one["indices"][0]) and torch.equal(rs["frames"][b], one["frames"][0])
+    with pytest.raises(ValueError):
+        sas.sample_mdf_ragged([clips[0], small[0]], encoder, K, W)                   # two frame sizes in one batch
 
 
 def test_plain_c_client_on_the_gpu(abi_check_exe):
