@@ -56,6 +56,9 @@ WORKLOADS = {
                     "(BASELINE configs[0]) as a single-clip latency probe"),
     "c2": dict(kind="mdf", clips=256, frames=128, K=16, W=8, H=224, Wd=224,
                desc="MDF batch of {clips} synthetic {frames}-frame 224x224 clips per GPU, K={K}, W={W} (BASELINE configs[1])"),
+    "c2r": dict(kind="mdf-ragged", clips=256, frames=128, K=16, W=8, H=224, Wd=224,
+                desc="MDF batch of {clips} synthetic 224x224 clips per GPU of DIFFERENT lengths (uniform in [T/2, 3T/2], T={frames}, "
+                     "same total frames as configs[1]) through the ragged call, K={K}, W={W}"),
     "c3": dict(kind="mif", clips=256, frames=128, K=8, W=0, H=224, Wd=224,
                desc="MIF question-conditioned sampling, {clips} clips x {frames} frames per GPU with synthetic question "
                     "embeddings, K={K} (BASELINE configs[2])"),
@@ -310,6 +313,16 @@ def run_ours(args):
     start, end = sharding.shard_range(n_total, rank, world)
     clips = synth.make_clips(range(start, end), T, device=dev, H=args.height, W=args.width)   # uint8, resident in HBM
     q = synth.question_embeddings(range(start, end), device=dev) if args.kind == "mif" else None
+    ragged_lengths = None
+    if args.kind == "mdf-ragged":                               # same frames, cut into clips of different lengths
+        g = torch.Generator().manual_seed(7 + rank)
+        lens = torch.randint(T // 2, 3 * T // 2 + 1, (B,), generator=g)
+        lens[-1] += B * T - int(lens.sum())                     # keep the total at B * T frames
+        while int(lens.min()) < K:                              # (never in practice; keeps every clip samplable)
+            lens[int(lens.argmin())] += K
+            lens[int(lens.argmax())] -= K
+        ragged_lengths = lens.tolist()
+        ragged_frames = clips.view(B * T, args.height, args.width, 3)
     dec, qids = None, None
     if args.kind == "mdf+vqa-full":
         dec = sas.GitDecoder(synth.random_git_decoder_state_dict(), max_rows=131072)
@@ -321,7 +334,9 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step():
-        if args.kind == "mif":
+        if args.kind == "mdf-ragged":
+            res = ops.mdf_sample_ragged(enc, ragged_frames, ragged_lengths, K, W, want_frames=True)
+        elif args.kind == "mif":
             res = sas.sample_mif_batch(clips, enc, q, K, args.ds_rate, want_frames=True)
             res["status"] = torch.zeros(B, dtype=torch.int32, device=dev)
         else:
