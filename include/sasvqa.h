@@ -138,6 +138,12 @@ int sasvqa_mdf_sample_ragged_u8(SasvqaEncoder* enc, const uint8_t* frames_hwc_de
                                 float* lcl_avg_or_null_dev, float* feats_or_null_dev, float* sampled_or_null_dev,
                                 void* stream);
 
+/* the same from HOST buffers (frames_hwc_host [sum T, H, W, 3]; pinned memory makes the copies asynchronous): whole clips
+ * are grouped up to chunk_frames frames and streamed through the double-buffered pipeline of sasvqa_mdf_sample_host */
+int sasvqa_mdf_sample_ragged_host(SasvqaEncoder* enc, const uint8_t* frames_hwc_host, int B, const int32_t* clip_offsets_host,
+                                  int H, int W, int K, int Wwin, int32_t* idx_host, int32_t* status_host,
+                                  float* sampled_or_null_host);
+
 /* ---- whole path, HOST buffers (the extraction loop extract_features.py:80-97 for a clip list) --
  * Streams clips host->device in double-buffered groups overlapped with compute, writes idx/status
  * (and, if not NULL, the sampled frames -- the rows of the reference's "sampled_frames" dataset)

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sasvqa_mdf_sample_f32": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
     "sasvqa_mdf_sample_u8_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
     "sasvqa_mdf_sample_ragged_u8": (c_int, [_p, _p, c_int, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),
+    "sasvqa_mdf_sample_ragged_host": (c_int, [_p, _p, c_int, _p, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_mdf_sample_host": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_mdf_sample_host_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "sasvqa_scorer_num_params": (c_uint64, [c_int, c_int]),

@@ -21,6 +21,7 @@ int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, c
 int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int, int, int32_t*, int32_t*,
                       float*, float*, float*, cudaStream_t);
 int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int, int, int32_t*, int32_t*, float*);
+int mdf_sample_ragged_host(SasvqaEncoder*, const uint8_t*, int, const int32_t*, int, int, int, int, int32_t*, int32_t*, float*);
 int mdf_sample_ragged_device(SasvqaEncoder*, const uint8_t*, const float*, int, const int32_t*, int, int, int, int, int32_t*,
                              int32_t*, float*, float*, float*, cudaStream_t);
 int encoder_set_projection(SasvqaEncoder*, const float*, const float*, const float*, const float*);
@@ -148,6 +149,10 @@ int sasvqa_mdf_sample_ragged_u8(SasvqaEncoder* enc, const uint8_t* frames, int B
                                 float* sampled, void* stream) {
     return mdf_sample_ragged_device(enc, frames, nullptr, B, clip_offsets_host, H, Wd, K, W, idx, status, lcl_avg, feats, sampled,
                                     S(stream));
+}
+int sasvqa_mdf_sample_ragged_host(SasvqaEncoder* enc, const uint8_t* frames_host, int B, const int32_t* clip_offsets_host, int H,
+                                  int Wd, int K, int W, int32_t* idx_host, int32_t* status_host, float* sampled_host) {
+    return mdf_sample_ragged_host(enc, frames_host, B, clip_offsets_host, H, Wd, K, W, idx_host, status_host, sampled_host);
 }
 int sasvqa_resize_crop_u8(const uint8_t* frames, int n_frames, int H, int Wd, uint8_t* out, void* stream) {
     return launch_resize_crop_u8(frames, n_frames, H, Wd, nullptr, 0, n_frames, out, S(stream));

@@ -762,4 +762,75 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
     return 0;
 }
 
+// Host-buffer pipeline for ragged batches: consecutive whole clips are grouped up to chunk_frames frames (a longer clip
+// is a group of its own); H2D, compute and D2H of consecutive groups overlap through the same two staging slots as
+// mdf_sample_host.  frames_host [sum T, H, W, 3] uint8, off_host [B + 1].
+int mdf_sample_ragged_host(SasvqaEncoder* e, const uint8_t* frames, int B, const int32_t* off_host, int H, int Wd, int K, int W,
+                           int32_t* idx_host, int32_t* status_host, float* sampled_host) {
+    SASVQA_REQUIRE(e != nullptr && idx_host != nullptr && status_host != nullptr && off_host != nullptr, "null argument");
+    SASVQA_REQUIRE(B >= 0 && K >= 1 && W >= -1, "bad B/K/W");
+    SASVQA_REQUIRE(H > 0 && Wd > 0, "bad frame size");
+    if (B == 0) return 0;
+    SASVQA_REQUIRE(off_host[0] == 0, "clip offsets must start at 0");
+    for (int b = 0; b < B; ++b) SASVQA_REQUIRE(off_host[b + 1] >= off_host[b], "clip offsets must not decrease");
+    SASVQA_REQUIRE(frames != nullptr || off_host[B] == 0, "null frames");
+    const size_t frame_bytes = (size_t)H * Wd * 3;
+    // groups of whole clips: [g_begin[i], g_begin[i+1])
+    std::vector<int> g_begin{0};
+    long long max_frames = 1;
+    int max_clips = 1;
+    for (int b = 0; b < B;) {
+        int j = b + 1;
+        while (j < B && (long long)off_host[j + 1] - off_host[b] <= e->chunk_frames) ++j;
+        max_frames = std::max<long long>(max_frames, off_host[j] - off_host[b]);
+        max_clips = std::max(max_clips, j - b);
+        g_begin.push_back(j);
+        b = j;
+    }
+    const size_t out_need = sampled_host ? (size_t)max_clips * K * kFrameElems * sizeof(float) : 0;
+    int rc;
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = grow((void**)&e->stage[i], &e->stage_cap[i], (size_t)max_frames * frame_bytes))) return rc;
+        if (out_need && (rc = grow((void**)&e->out_stage[i], &e->out_stage_cap[i], out_need))) return rc;
+        if ((rc = grow((void**)&e->idx_stage[i], &e->idx_stage_cap[i], (size_t)max_clips * (K + 1) * sizeof(int32_t)))) return rc;
+    }
+    std::vector<int32_t> off_g;
+    const int n_groups = (int)g_begin.size() - 1;
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int slot = gi & 1;
+        const int b0 = g_begin[gi], nb = g_begin[gi + 1] - b0;
+        const long long f0 = off_host[b0], nf = off_host[b0 + nb] - f0;
+        off_g.assign((size_t)nb + 1, 0);
+        for (int i = 0; i <= nb; ++i) off_g[i] = off_host[b0 + i] - (int32_t)f0;
+        if (gi >= 2) SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->h2d_stream, e->ev_comp[slot], 0));
+        if (nf > 0)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->stage[slot], frames + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes,
+                                              cudaMemcpyHostToDevice, e->h2d_stream));
+        SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_in[slot], e->h2d_stream));
+        SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->compute_stream, e->ev_in[slot], 0));
+        if (gi >= 2) SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->compute_stream, e->ev_out[slot], 0));
+        int32_t* d_idx = e->idx_stage[slot];
+        int32_t* d_status = d_idx + (size_t)max_clips * K;
+        float* d_out = sampled_host ? e->out_stage[slot] : nullptr;
+        if ((rc = mdf_sample_ragged_device(e, e->stage[slot], nullptr, nb, off_g.data(), H, Wd, K, W, d_idx, d_status, nullptr,
+                                           nullptr, d_out, e->compute_stream)))
+            return rc;
+        SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_comp[slot], e->compute_stream));
+        SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->ev_comp[slot], 0));
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host + (size_t)b0 * K, d_idx, (size_t)nb * K * sizeof(int32_t),
+                                          cudaMemcpyDeviceToHost, e->d2h_stream));
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(status_host + b0, d_status, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                          e->d2h_stream));
+        if (sampled_host)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(sampled_host + (size_t)b0 * K * kFrameElems, d_out,
+                                              (size_t)nb * K * kFrameElems * sizeof(float), cudaMemcpyDeviceToHost,
+                                              e->d2h_stream));
+        SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_out[slot], e->d2h_stream));
+    }
+    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
+    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->compute_stream));
+    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->h2d_stream));
+    return 0;
+}
+
 }  // namespace sasvqa

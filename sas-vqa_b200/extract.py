@@ -54,8 +54,7 @@ def generate_h5(clips, model, K: int, W: int, h5_outfile: str, sampling_strategy
                     else:
                         if not torch.cuda.is_available():
                             raise ops._capi.SasvqaError("generate_h5 needs a CUDA device (no CPU fallback)")
-                        res = sampler.sample_mdf_ragged(group, enc, K, W)
-                        res = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in res.items()}
+                        res = sampler.sample_mdf_ragged([c.cpu() for c in group], enc, K, W)      # host-buffer pipeline
                     st = res["status"]
                     if bool((st == ops.STATUS_TOO_FEW).any()):                       # utils.py:92: topk raises
                         raise RuntimeError("selected index k out of range")

@@ -339,6 +339,32 @@ def mdf_sample_ragged(enc: FrameEncoder, frames: torch.Tensor, lengths, K: int, 
     return dict(indices=idx, status=status, lcl_avg=lcl, feats=feats, frames=sampled, offsets=off)
 
 
+def mdf_sample_ragged_host(enc: FrameEncoder, frames_host: torch.Tensor, lengths, K: int, W: int, want_frames: bool = True) -> dict:
+    """Ragged batch from host memory: ``frames_host`` [sum(lengths), H, W, 3] uint8 (pinned for full speed).  Results
+    land in (pinned) host tensors: dict(indices [B, K], status [B], frames [B, K, 3, 224, 224] | None, offsets)."""
+    if frames_host.is_cuda or frames_host.dtype != torch.uint8:
+        raise TypeError("frames_host must be a uint8 CPU tensor")
+    if frames_host.dim() != 4 or frames_host.shape[-1] != 3:
+        raise ValueError(f"frames_host must be [sum T, H, W, 3], got {tuple(frames_host.shape)}")
+    frames_host = frames_host.contiguous()
+    lens = torch.as_tensor(lengths, dtype=torch.int64).reshape(-1)
+    if int(lens.sum()) != int(frames_host.shape[0]) or bool((lens < 0).any()):
+        raise ValueError(f"lengths sum to {int(lens.sum())}, frames_host holds {int(frames_host.shape[0])}")
+    B = int(lens.numel())
+    off = torch.zeros(B + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(lens, 0).to(torch.int32)
+    H, Wd = int(frames_host.shape[1]), int(frames_host.shape[2])
+    pin = torch.cuda.is_available()
+    idx = torch.empty(B, K, dtype=torch.int32, pin_memory=pin)
+    status = torch.empty(B, dtype=torch.int32, pin_memory=pin)
+    sampled = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, pin_memory=pin) if want_frames else None
+    with torch.cuda.device(enc.device):
+        _capi.check(_capi.lib().sasvqa_mdf_sample_ragged_host(enc.handle, frames_host.data_ptr(), B, off.data_ptr(), H, Wd, int(K),
+                                                              int(W), idx.data_ptr(), status.data_ptr(), _capi.ptr(sampled)),
+                    "sasvqa_mdf_sample_ragged_host")
+    return dict(indices=idx, status=status, frames=sampled, offsets=off)
+
+
 def mdf_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, K: int, W: int, idx_out: torch.Tensor = None,
                     status_out: torch.Tensor = None, frames_out: torch.Tensor = None, want_frames: bool = True) -> dict:
     """clips_host: [B, T, H, W, 3] uint8 in (ideally pinned) host memory.  Results land in host tensors."""

@@ -81,7 +81,8 @@ def sample_mdf_batch(clips: torch.Tensor, model, K: int = 16, W: int = 8, debug_
 def sample_mdf_ragged(clips, model, K: int = 16, W: int = 8, debug_counter=None, want_frames: bool = True,
                       want_aux: bool = False) -> dict:
     """Batched MDF over clips of DIFFERENT lengths (one frame size): ``clips`` is a sequence of uint8 tensors
-    [T_i, H, W, 3] (CPU or GPU; concatenated and moved to the GPU here).  One library call for the whole batch -- the
+    [T_i, H, W, 3] (GPU clips are concatenated on the device; CPU clips go through one pinned buffer and the
+    pipelined host-buffer call, results then come back as host tensors).  One library call for the whole batch -- the
     encoder is frame-batched, the selection kernels take per-clip offsets -- with per clip exactly the result of the
     reference's one-video-per-call loop (extract_features.py:80-97): empty clips give zero frames ('Zeros'), W == -1
     adapts per clip, the fallback counts a 'Failure'.  Returns the dict of ``sample_mdf_batch`` with per-frame
@@ -94,8 +95,14 @@ def sample_mdf_ragged(clips, model, K: int = 16, W: int = 8, debug_counter=None,
     shapes = {tuple(c.shape[1:]) for c in clips}
     if len(shapes) != 1:
         raise ValueError(f"all clips of a ragged batch must share one frame size, got {sorted(shapes)}")
-    frames = torch.cat([c.to(enc.device) for c in clips], dim=0)
-    res = ops.mdf_sample_ragged(enc, frames, lengths, K, W, want_frames=want_frames, want_aux=want_aux)
+    if all(not c.is_cuda for c in clips) and not want_aux:
+        # host clips: one pinned staging buffer, then the pipelined host-buffer call (results in host tensors)
+        host = torch.empty((sum(lengths),) + tuple(clips[0].shape[1:]), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        torch.cat(clips, dim=0, out=host)
+        res = ops.mdf_sample_ragged_host(enc, host, lengths, K, W, want_frames=want_frames)
+    else:
+        frames = torch.cat([c.to(enc.device) for c in clips], dim=0)
+        res = ops.mdf_sample_ragged(enc, frames, lengths, K, W, want_frames=want_frames, want_aux=want_aux)
     if debug_counter is not None:
         st = res["status"].cpu()
         debug_counter["Failure"] += int((st == ops.STATUS_FALLBACK).sum())

@@ -547,6 +547,14 @@ def test_ragged_batch_equals_one_call_per_clip(encoder, W):
             assert torch.equal(res["frames"][b], one["frames"][0])
         n_fail += int(one["status"][0]) == ops.STATUS_FALLBACK
     assert dc == {"Failure": n_fail, "Zeros": 1}
+    # CPU clips without aux outputs take the host-buffer pipeline (groups of whole clips up to chunk_frames = 96 frames:
+    # [40, 0, 17] [64, 5, 23] [128] [9, 6]); same answers, in host tensors
+    host = sas.sample_mdf_ragged(clips, encoder, K, W)
+    assert not host["indices"].is_cuda and torch.equal(host["status"], res["status"].cpu())
+    ok = (res["status"] != ops.STATUS_TOO_FEW).cpu()
+    assert torch.equal(host["indices"][ok], res["indices"].cpu()[ok]) and torch.equal(host["frames"][ok], res["frames"].cpu()[ok])
+    empty = sas.sample_mdf_ragged([torch.zeros(0, 224, 224, 3, dtype=torch.uint8)] * 2, encoder, K, W)
+    assert empty["status"].tolist() == [ops.STATUS_EMPTY] * 2 and float(empty["frames"].abs().sum()) == 0.0
     if W == 3:                              # T = 5 < K = 6 on the fallback path: the reference's topk raises
         assert int(res["status"][4]) == ops.STATUS_TOO_FEW
     else:                                   # T // 20 = 0 for the short clips: a zero-width window re-offers the first
@@ -557,7 +565,9 @@ def test_ragged_batch_equals_one_call_per_clip(encoder, W):
     rs = sas.sample_mdf_ragged(small, encoder, 4, 2)
     for b, clip in enumerate(small):
         one = sas.sample_mdf_batch(clip.unsqueeze(0).to(DEV), encoder, 4, 2)
-        assert torch.equal(rs["indices"][b], one["indices"][0]) and torch.equal(rs["frames"][b], one["frames"][0])
+        assert torch.equal(rs["indices"][b].cpu(), one["indices"][0].cpu()) and torch.equal(rs["frames"][b].cpu(), one["frames"][0].cpu())
+    rd = sas.sample_mdf_ragged([c.to(DEV) for c in small], encoder, 4, 2)         # GPU clips: the device entry point
+    assert rd["indices"].is_cuda and torch.equal(rd["indices"].cpu(), rs["indices"]) and torch.equal(rd["frames"].cpu(), rs["frames"])
     with pytest.raises(ValueError):
         sas.sample_mdf_ragged([clips[0], small[0]], encoder, K, W)                   # two frame sizes in one batch
 
