@@ -238,6 +238,14 @@ int sasvqa_git_vqa_logits_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const f
 int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
                             const int32_t* input_ids_dev, const int32_t* labels_dev, int L, float* loss_dev,
                             float* logits_or_null_dev, void* stream);
+/* greedy answer decoding, the reference's evaluation path `self.model.generate(**inputs, max_length=50)`
+ * (modeling.py:330-333; HF greedy search): prompt [B, L0] int32 (equal lengths, no padding) -> out_ids [B, max_length]
+ * int32 = the prompt followed by one argmax token per step; a sequence that produced eos_token_id emits pad_token_id from
+ * then on (HF stops once every sequence has finished: trim the all-pad tail).  The visual rows are run once per group
+ * and their per-block keys / values cached; every step runs the text rows against the cache. */
+int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
+                                const int32_t* prompt_ids_dev, int L0, int max_length, int eos_token_id, int pad_token_id,
+                                int32_t* out_ids_dev, void* stream);
 /* inspection: fp32 stream [B*K*197 + B*L, 768] after `n_layers` blocks (all visual rows first, then all text rows);
  * the call must fit one pass */
 int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,

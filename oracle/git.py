@@ -90,3 +90,23 @@ class GitVqaOracle:
         shifted = logits[:, :-1, :].contiguous()
         tgt = torch.as_tensor(labels).long()[:, 1:].contiguous()
         return F.cross_entropy(shifted.view(-1, shifted.shape[-1]), tgt.view(-1))
+
+    @torch.no_grad()
+    def generate(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, max_length: int = 50, eos_token_id: int = 102,
+                 pad_token_id: int = 0):
+        """Greedy search as HF ``generate`` runs it for ``modeling.py:333`` (``do_sample=False``, one beam): append
+        ``argmax(logits[:, -1])`` until every sequence has emitted eos or ``max_length`` is reached; finished sequences
+        are padded.  Also returns, per step, the top-2 logit margin of every sequence (for tie-aware comparisons)."""
+        ids = torch.as_tensor(input_ids).long().clone()
+        B = ids.shape[0]
+        done = torch.zeros(B, dtype=torch.bool)
+        margins = []
+        while ids.shape[1] < max_length and not bool(done.all()):
+            logits = self(pixel_values, ids)[:, -1, :]
+            top2 = logits.topk(2, dim=-1).values
+            margins.append((top2[:, 0] - top2[:, 1]).masked_fill(done, float("inf")))
+            nxt = logits.argmax(dim=-1)
+            nxt = torch.where(done, torch.full_like(nxt, pad_token_id), nxt)
+            ids = torch.cat([ids, nxt[:, None]], dim=1)
+            done |= nxt == eos_token_id
+        return ids, (torch.stack(margins, dim=1) if margins else torch.zeros(B, 0))

@@ -323,8 +323,23 @@ def gen_git_vqa():
         shifted_logits = out.logits[:, K * 197:-1, :].contiguous()
         loss = torch.nn.CrossEntropyLoss()(shifted_logits.view(-1, synth.GIT_VOCAB), labels[:, 1:].contiguous().view(-1))
         print("git vqa: loss", float(loss), "restatement", float(git_oracle.GitVqaOracle(enc_sd, psd, dsd).loss(frames, ids, labels)))
+    # greedy decoding as the reference's evaluation runs it (modeling.py:333: model.generate(**inputs, max_length=...)):
+    # argmax of HF's forward, step by step WITHOUT its KV cache, on a 4-token prompt, against the restated greedy loop.
+    # (HF 5.5's cached generate is not used as the pin: from the second cached step on it departs from the same model's
+    # uncached forward -- checked here, it picks 487 where the forward's argmax is 5682 at a top-2 margin of 0.35 -- so it
+    # is not a faithful execution of the model the reference was written against.)
+    prompt = ids[:, :4].contiguous()
+    with torch.no_grad():
+        hf_gen = prompt.clone()
+        while hf_gen.shape[1] < 12:
+            step = model(input_ids=hf_gen, attention_mask=torch.ones_like(hf_gen), pixel_values=frames, use_cache=False)
+            hf_gen = torch.cat([hf_gen, step.logits[:, -1].argmax(dim=-1, keepdim=True)], dim=1)
+        my_gen, margins = git_oracle.GitVqaOracle(enc_sd, psd, dsd).generate(frames, prompt, max_length=12)
+    print("git vqa: greedy on HF's forward", hf_gen.tolist(), "restatement equal:", torch.equal(hf_gen, my_gen),
+          "min top-2 margin", float(margins.min()))
     top = logits.topk(5, dim=-1)
-    np.savez_compressed(os.path.join(GOLD, "git_vqa_hf.npz"), labels=labels.numpy(), loss=np.float32(loss), clip_ids=np.asarray([60, 61]), K=np.int64(K),
+    np.savez_compressed(os.path.join(GOLD, "git_vqa_hf.npz"), labels=labels.numpy(), loss=np.float32(loss),
+                        gen_prompt=prompt.numpy(), gen_ids=hf_gen.numpy(), gen_margins=margins.numpy(), clip_ids=np.asarray([60, 61]), K=np.int64(K),
                         input_ids=ids.numpy(), attention_mask=mask.numpy(), logits_probe=logits[:, :, ::61].numpy(),
                         logits_row=logits[0, 3].numpy(), top5_idx=top.indices.numpy(), top5_val=top.values.numpy())
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "sasvqa_git_decoder_vocab_padded": (c_int, [_p]),
     "sasvqa_git_vqa_logits_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, c_int, _p, _p]),
     "sasvqa_git_vqa_loss_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, _p, c_int, _p, _p, _p]),
+    "sasvqa_git_vqa_generate_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, c_int, c_int, c_int, c_int, _p, _p]),
     "sasvqa_git_vqa_hidden_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, c_int, c_int, _p, _p]),
     "sasvqa_test_attention_git": (c_int, [_p, c_int, c_int, c_int, _p, _p]),
     "sasvqa_test_attention_varlen": (c_int, [_p, _p, c_int, c_int, _p, _p]),

@@ -227,14 +227,17 @@ constexpr int GIT_QBLOCK = GIT_WARPS * 16;
 
 __global__ void __launch_bounds__(GIT_WARPS * 32, 2)
 attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_samples, int n_vis, int L,
-                     int q_blocks, int q_block0) {
+                     int q_blocks, int q_block0, const __nv_bfloat16* __restrict__ vis_kv, long long txt_row0) {
     __shared__ __align__(128) uint8_t kv[2][2][64 * 128];              // [buffer][K | V][64 keys x 64 d bf16]
     const int S = n_vis + L;
     const int qb = q_block0 + blockIdx.x % q_blocks;             // q_block0 > 0: only the blocks that hold text rows
     const int head = (blockIdx.x / q_blocks) % kHeads;
     const int smp = blockIdx.x / (q_blocks * kHeads);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long vis_base = (long long)smp * n_vis, txt_base = (long long)n_samples * n_vis + (long long)smp * L;
+    // vis_kv != nullptr (incremental decoding): qkv / out hold the TEXT rows only (sample s at txt_row0 + s * L) and the
+    // visual keys and values come from the per-layer cache vis_kv [n * n_vis, k | v] written by the prefill pass
+    const bool cached = vis_kv != nullptr;
+    const long long vis_base = (long long)smp * n_vis, txt_base = txt_row0 + (long long)smp * L;
     auto row_of = [&](int j) -> long long { return j < n_vis ? vis_base + j : txt_base + (j - n_vis); };
     const int q0 = qb * GIT_QBLOCK;
     const int q_last = min(q0 + GIT_QBLOCK, S) - 1;                      // last real query row of this block
@@ -248,9 +251,16 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
         const uint32_t v_smem = (uint32_t)__cvta_generic_to_shared(kv[buf][1]);
         for (int i = threadIdx.x; i < 64 * 8; i += GIT_WARPS * 32) {
             const int r = i >> 3, c = i & 7;
-            const long long row = row_of(min(chunk * 64 + r, S - 1));    // rows past the sequence: any real row (masked)
-            cp_async16(k_smem + tile_off(r, c), kbase + row * kQkv + c * 8);
-            cp_async16(v_smem + tile_off(r, c), vbase + row * kQkv + c * 8);
+            const int j = min(chunk * 64 + r, S - 1);                    // rows past the sequence: any real row (masked)
+            const long long row = row_of(j);
+            if (cached && j < n_vis) {
+                const __nv_bfloat16* src = vis_kv + row * (2 * kHidden) + head * kHeadDim + c * 8;
+                cp_async16(k_smem + tile_off(r, c), src);
+                cp_async16(v_smem + tile_off(r, c), src + kHidden);
+            } else {
+                cp_async16(k_smem + tile_off(r, c), kbase + row * kQkv + c * 8);
+                cp_async16(v_smem + tile_off(r, c), vbase + row * kQkv + c * 8);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -258,7 +268,11 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     // this warp's 16 query rows
     const int g = lane >> 2, t = lane & 3;
     const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
-    const int r0c = min(r0, S - 1), r1c = min(r1, S - 1);
+    int r0c = min(r0, S - 1), r1c = min(r1, S - 1);
+    if (cached) {                                                        // visual query rows do not exist in this mode
+        r0c = max(r0c, n_vis);
+        r1c = max(r1c, n_vis);
+    }
     const int lim0 = r0c < n_vis ? n_vis : r0c + 1, lim1 = r1c < n_vis ? n_vis : r1c + 1;
     const int w_last = min(q0 + warp * 16 + 15, S - 1);
     const int warp_limit = w_last < n_vis ? n_vis : w_last + 1;          // warp-uniform
@@ -309,8 +323,8 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     __nv_bfloat16* o1 = out + row_of(r1c) * kHidden + head * kHeadDim + 2 * t;
 #pragma unroll
     for (int dt = 0; dt < 8; ++dt) {
-        if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
-        if (r1 < S) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+        if (r0 < S && r0 == r0c) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+        if (r1 < S && r1 == r1c) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
     }
 }
 
@@ -318,9 +332,12 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 // text_only != 0: only the query blocks that contain text rows are computed (the last decoder block when nobody reads
 // the visual rows afterwards); visual rows that share a block with the first text rows are recomputed, harmlessly
+// vis_kv != nullptr: incremental decoding -- qkv / out are the text rows only ([n * L, .], sample-major), the visual keys
+// and values are read from the cache [n * n_vis, 1536] (k | v) of this layer; only text query blocks run
 int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, int text_only,
-                         cudaStream_t s) {
+                         cudaStream_t s, const __nv_bfloat16* vis_kv) {
     if (n_samples == 0) return 0;
+    if (vis_kv != nullptr) text_only = 1;
     SASVQA_REQUIRE(n_vis >= 1 && L >= 0, "the visual prefix must hold at least one token");
     SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
     const int all_blocks = (n_vis + L + GIT_QBLOCK - 1) / GIT_QBLOCK;
@@ -329,7 +346,9 @@ int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_sam
     if (q_blocks <= 0) return 0;                                  // text_only with L == 0
     const long long grid = (long long)n_samples * kHeads * q_blocks;
     SASVQA_REQUIRE(grid < 2147483647LL, "too many attention blocks for one launch");
-    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks, q_block0);
+    const long long txt_row0 = vis_kv != nullptr ? 0 : (long long)n_samples * n_vis;
+    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks, q_block0, vis_kv,
+                                                                   txt_row0);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

@@ -35,6 +35,8 @@ void git_decoder_destroy(SasvqaGitDecoder*);
 int git_decoder_vocab_padded(const SasvqaGitDecoder*);
 int git_vqa_logits(SasvqaGitDecoder*, SasvqaEncoder*, const float*, int, int, const int32_t*, int, float*, int, float*,
                    const int32_t*, float*, cudaStream_t);
+int git_vqa_generate(SasvqaGitDecoder*, SasvqaEncoder*, const float*, int, int, const int32_t*, int, int, int, int, int32_t*,
+                     cudaStream_t);
 uint64_t scorer_num_params(int, int);
 int scorer_create(const float*, uint64_t, int, int, int, SasvqaScorer**);
 void scorer_destroy(SasvqaScorer*);
@@ -227,6 +229,10 @@ int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const flo
     SASVQA_REQUIRE(loss != nullptr && labels != nullptr, "null loss / labels");
     SASVQA_REQUIRE(B >= 1, "the loss of an empty batch is undefined");
     return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits_or_null, 1 << 30, nullptr, labels, loss, S(stream));
+}
+int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* prompt,
+                                int L0, int max_length, int eos_token_id, int pad_token_id, int32_t* out_ids, void* stream) {
+    return git_vqa_generate(dec, enc, frames, B, K, prompt, L0, max_length, eos_token_id, pad_token_id, out_ids, S(stream));
 }
 int sasvqa_test_attention_git(const uint16_t* qkv, int n_samples, int n_vis, int L, uint16_t* out, void* stream) {
     SASVQA_REQUIRE(n_samples == 0 || (qkv && out), "null argument");

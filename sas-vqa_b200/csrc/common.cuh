@@ -128,7 +128,7 @@ int launch_gather_f32(const float* frames, const int32_t* idx, int B, int T, int
 int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int32_t* cu_seqlens_dev, int row_base,
                             int n_seqs, int max_len, cudaStream_t s);
 int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, int text_only,
-                         cudaStream_t s);
+                         cudaStream_t s, const __nv_bfloat16* vis_kv = nullptr);
 int launch_layernorm_post(float* x, __nv_bfloat16* h, long long rows, const float* gamma, const float* beta, float eps,
                           cudaStream_t s);
 int launch_embed_layernorm(const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens, int row_base,

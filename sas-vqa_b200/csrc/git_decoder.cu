@@ -126,6 +126,61 @@ __global__ void __launch_bounds__(256) ce_mean_kernel(const float* __restrict__ 
     if (threadIdx.x == 0) loss[0] = (float)(acc[0] / (double)cnt[0]);      // no valid label: 0 / 0 = NaN, as torch
 }
 
+// Greedy decoding step (HF generate, greedy search): next = argmax(logits[row]) (lowest index among equals); a sequence that
+// has produced eos keeps emitting pad.  One CTA per sample; writes ids[s, pos] and updates finished[s].
+__global__ void __launch_bounds__(256) greedy_next_kernel(const float* __restrict__ logits, int vocab, int vocab_pad,
+                                                           int32_t* __restrict__ ids, int Lmax, int pos, int eos, int pad,
+                                                           int32_t* __restrict__ finished) {
+    __shared__ float bv[8];
+    __shared__ int bi[8];
+    const int smp = blockIdx.x;
+    const float* row = logits + (long long)smp * vocab_pad;
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int i = threadIdx.x; i < vocab; i += 256) {
+        const float v = row[i];
+        if (v > best || arg == 0x7fffffff) {        // strided scan: i increases, so '>' keeps the lowest index per thread
+            best = v;
+            arg = i;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ov > best || (ov == best && oi < arg)) {
+            best = ov;
+            arg = oi;
+        }
+    }
+    if (lane == 0) {
+        bv[warp] = best;
+        bi[warp] = arg;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (bv[w] > best || (bv[w] == best && bi[w] < arg)) {
+                best = bv[w];
+                arg = bi[w];
+            }
+        const int done = finished[smp];
+        const int tok = done ? pad : arg;
+        ids[(long long)smp * Lmax + pos] = tok;
+        if (!done && tok == eos) finished[smp] = 1;
+    }
+}
+__global__ void init_generate_kernel(const int32_t* __restrict__ prompt, int L0, int32_t* __restrict__ ids, int Lmax, int pad,
+                                     int32_t* __restrict__ finished, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * Lmax) {
+        const int smp = i / Lmax, p = i - smp * Lmax;
+        ids[i] = p < L0 ? prompt[(long long)smp * L0 + p] : pad;
+    }
+    if (i < n) finished[i] = 0;
+}
+
 struct GitLayer {
     __nv_bfloat16 *w_qkv, *w_out, *w_fc1, *w_fc2;
     float *b_qkv, *b_out, *ln1_g, *ln1_b, *b_fc1, *b_fc2, *ln2_g, *ln2_b;
@@ -159,6 +214,15 @@ struct SasvqaGitDecoder {
     // loss path scratch: logits of one group, per-row losses of the whole call
     float* logits_scratch = nullptr;
     size_t logits_cap = 0;
+    // incremental decoding: per-layer k | v of the visual rows of one group, ids / flags / last-row scratch
+    __nv_bfloat16* kv_cache = nullptr;   // [n_layers][kv_rows, 1536]
+    size_t kv_cap = 0;
+    int32_t* gen_ids = nullptr;          // [group, Lmax]
+    size_t gen_ids_cap = 0;
+    int32_t* gen_done = nullptr;         // [group]
+    size_t gen_done_cap = 0;
+    __nv_bfloat16* last_h = nullptr;     // [group, 768] hidden state of the newest position
+    size_t last_h_cap = 0;
     float* row_loss = nullptr;
     size_t row_loss_cap = 0;
     int32_t* row_valid = nullptr;
@@ -198,6 +262,7 @@ void git_decoder_destroy(SasvqaGitDecoder* d) {
     cudaFree(d->arena_bf16); cudaFree(d->arena_f32);
     cudaFree(d->x); cudaFree(d->h); cudaFree(d->big); cudaFree(d->cu_dev);
     cudaFree(d->logits_scratch); cudaFree(d->row_loss); cudaFree(d->row_valid);
+    cudaFree(d->kv_cache); cudaFree(d->gen_ids); cudaFree(d->gen_done); cudaFree(d->last_h);
     delete d;
 }
 
@@ -448,6 +513,127 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
         ce_mean_kernel<<<1, 256, 0, s>>>(d->row_loss, d->row_valid, B * (L - 1), loss_or_null);
         SASVQA_CUDA_CHECK(cudaGetLastError());
         count_launch();
+    }
+    return 0;
+}
+
+namespace {
+
+// one decoder block over rows [0, M) of the workspace; the attention is supplied by the caller
+template <class Attention>
+int run_block(SasvqaGitDecoder* d, GitLayer& Ly, long long M, Attention&& attention, cudaStream_t s) {
+    int rc;
+    GemmArgs g{};
+    g.A = d->h; g.B = Ly.w_qkv; g.M = (int)M; g.N = kQkv; g.K = kHidden;
+    g.epilogue = EPI_BIAS_BF16; g.bias = Ly.b_qkv; g.out_bf16 = d->big;
+    if ((rc = dgemm(d, g, &d->m_h, &Ly.m_qkv, &d->m_out_qkv, s))) return rc;
+    rc = attention();                                           // reads big (q|k|v), writes h
+    if (rc < 0) return 0;                                       // < 0: the caller only wanted the projection
+    if (rc) return rc;
+    g = GemmArgs{};
+    g.A = d->h; g.B = Ly.w_out; g.M = (int)M; g.N = kHidden; g.K = kHidden;
+    g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_out; g.out_f32 = d->x;
+    if ((rc = dgemm(d, g, &d->m_h, &Ly.m_out, &d->m_out_x, s))) return rc;
+    if ((rc = launch_layernorm_post(d->x, d->h, M, Ly.ln1_g, Ly.ln1_b, kGitLnEps, s))) return rc;
+    g = GemmArgs{};
+    g.A = d->h; g.B = Ly.w_fc1; g.M = (int)M; g.N = kFfn; g.K = kHidden;
+    g.epilogue = EPI_BIAS_ERF_GELU_BF16; g.bias = Ly.b_fc1; g.out_bf16 = d->big;
+    if ((rc = dgemm(d, g, &d->m_h, &Ly.m_fc1, &d->m_out_fc1, s))) return rc;
+    g = GemmArgs{};
+    g.A = d->big; g.B = Ly.w_fc2; g.M = (int)M; g.N = kHidden; g.K = kFfn;
+    g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_fc2; g.out_f32 = d->x;
+    if ((rc = dgemm(d, g, &d->m_big_fc, &Ly.m_fc2, &d->m_out_x, s))) return rc;
+    return launch_layernorm_post(d->x, d->h, M, Ly.ln2_g, Ly.ln2_b, kGitLnEps, s);
+}
+
+}  // namespace
+
+// Greedy answer decoding, what the reference's evaluation runs: `self.model.generate(**inputs, max_length=50)`
+// (src/modeling/modeling.py:330-333, HF greedy search on MyGitForCausalLM).  prompt [B, L0] int32 (equal lengths, no
+// padding), out_ids [B, max_length] int32: the prompt, then one argmax token per step; after eos a sequence emits pad.
+// The visual rows never depend on the text (they only see each other), so they are run ONCE per group -- five full
+// blocks plus the sixth block's k|v projection -- and every block's visual keys and values are cached; a step then runs the
+// text rows alone (all max_length positions at a fixed stride: causal masking makes the not-yet-written ones harmless)
+// against the cache.  No early exit on "all finished": the step count is fixed, the tail is pad.
+int git_vqa_generate(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* prompt, int L0,
+                     int max_length, int eos, int pad, int32_t* out_ids, cudaStream_t s) {
+    SASVQA_REQUIRE(d != nullptr && enc != nullptr && B >= 0 && K >= 1, "bad arguments");
+    SASVQA_REQUIRE(L0 >= 1 && max_length >= L0 && max_length <= kGitMaxPos, "need 1 <= prompt length <= max_length <= 1024");
+    if (B == 0) return 0;
+    SASVQA_REQUIRE(frames != nullptr && prompt != nullptr && out_ids != nullptr, "null argument");
+    const int n_vis = K * kTokens, Lmax = max_length;
+    SASVQA_REQUIRE((long long)n_vis <= d->max_rows && (long long)Lmax <= d->max_rows, "one sample does not fit the workspace");
+    const int group = (int)std::min<long long>(B, std::min<long long>(d->max_rows / n_vis, d->max_rows / Lmax));
+    int rc;
+    const size_t kv_rows = (size_t)group * n_vis;
+    if ((rc = dgrow((void**)&d->kv_cache, &d->kv_cap, (size_t)d->n_layers * kv_rows * 2 * kHidden * sizeof(__nv_bfloat16)))) return rc;
+    if ((rc = dgrow((void**)&d->gen_ids, &d->gen_ids_cap, (size_t)group * Lmax * sizeof(int32_t)))) return rc;
+    if ((rc = dgrow((void**)&d->gen_done, &d->gen_done_cap, (size_t)group * sizeof(int32_t)))) return rc;
+    if ((rc = dgrow((void**)&d->last_h, &d->last_h_cap, (size_t)std::max(group, 1) * kHidden * sizeof(__nv_bfloat16)))) return rc;
+    if ((rc = dgrow((void**)&d->logits_scratch, &d->logits_cap, (size_t)group * d->vocab_pad * sizeof(float)))) return rc;
+    if ((size_t)(group + 1) * sizeof(int32_t) > d->cu_cap) {
+        if (d->cu_dev) SASVQA_CUDA_CHECK(cudaFree(d->cu_dev));
+        d->cu_dev = nullptr;
+        d->cu_cap = 0;
+        SASVQA_CUDA_CHECK(cudaMalloc((void**)&d->cu_dev, (size_t)(group + 1) * sizeof(int32_t)));
+        d->cu_cap = (size_t)(group + 1) * sizeof(int32_t);
+    }
+    std::vector<int32_t> cu((size_t)group + 1);
+    for (int b0 = 0; b0 < B; b0 += group) {
+        const int n = std::min(group, B - b0);
+        const long long rows_vis = (long long)n * n_vis, rows_txt = (long long)n * Lmax;
+        // ---- prefill: the visual rows through the blocks, k|v of every block into the cache
+        if ((rc = visual_tokens(enc, nullptr, frames + (size_t)b0 * K * kFrameElems, n * K, 1, d->x, s))) return rc;
+        rows_to_bf16_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(d->x), reinterpret_cast<uint4*>(d->h),
+                                                    rows_vis * kHidden / 8);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        for (int l = 0; l < d->n_layers; ++l) {
+            __nv_bfloat16* cache = d->kv_cache + (size_t)l * kv_rows * 2 * kHidden;
+            const bool last = l == d->n_layers - 1;
+            auto att = [&]() -> int {
+                SASVQA_CUDA_CHECK(cudaMemcpy2DAsync(cache, 2 * kHidden * sizeof(__nv_bfloat16), d->big + kHidden,
+                                                    kQkv * sizeof(__nv_bfloat16), 2 * kHidden * sizeof(__nv_bfloat16),
+                                                    (size_t)rows_vis, cudaMemcpyDeviceToDevice, s));
+                if (last) return -1;                            // nobody reads the visual rows after the last block
+                return launch_attention_git(d->big, d->h, n, n_vis, 0, 0, s);
+            };
+            if ((rc = run_block(d, d->L[l], rows_vis, att, s))) return rc;
+        }
+        // ---- decode: text rows only, sample i at rows [i * Lmax, (i + 1) * Lmax)
+        init_generate_kernel<<<(unsigned)((rows_txt + 255) / 256), 256, 0, s>>>(prompt + (size_t)b0 * L0, L0, d->gen_ids, Lmax, pad,
+                                                                                 d->gen_done, n);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        for (int i = 0; i <= n; ++i) cu[i] = (int32_t)((long long)i * Lmax);
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(d->cu_dev, cu.data(), ((size_t)n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        for (int pos = L0; pos < Lmax; ++pos) {                 // the token at `pos` comes from the row at pos - 1
+            if ((rc = launch_embed_layernorm(d->gen_ids, nullptr, d->cu_dev, 0, n, Lmax, d->vocab, 1, d->word, d->pos, d->zero_row,
+                                             d->emb_g, d->emb_b, kGitLnEps, d->x, d->h, s)))
+                return rc;
+            for (int l = 0; l < d->n_layers; ++l) {
+                const __nv_bfloat16* cache = d->kv_cache + (size_t)l * kv_rows * 2 * kHidden;
+                auto att = [&]() -> int { return launch_attention_git(d->big, d->h, n, n_vis, Lmax, 1, s, cache); };
+                if ((rc = run_block(d, d->L[l], rows_txt, att, s))) return rc;
+            }
+            SASVQA_CUDA_CHECK(cudaMemcpy2DAsync(d->last_h, kHidden * sizeof(__nv_bfloat16), d->h + (size_t)(pos - 1) * kHidden,
+                                                (size_t)Lmax * kHidden * sizeof(__nv_bfloat16), kHidden * sizeof(__nv_bfloat16),
+                                                (size_t)n, cudaMemcpyDeviceToDevice, s));
+            SASVQA_CUDA_CHECK(cudaMemsetAsync(d->logits_scratch, 0, (size_t)n * d->vocab_pad * sizeof(float), s));
+            GemmArgs g{};
+            g.A = d->last_h; g.B = d->w_head; g.M = n; g.N = d->vocab_pad; g.K = kHidden;
+            g.epilogue = EPI_BIAS_RESID_F32; g.bias = d->b_head; g.out_f32 = d->logits_scratch;
+            CUtensorMap ma, mo;
+            if ((rc = make_tensor_map_bf16_kmajor(&ma, d->last_h, (uint64_t)n, kHidden, 128))) return rc;
+            if ((rc = make_tensor_map_out(&mo, d->logits_scratch, (uint64_t)n, (uint64_t)d->vocab_pad, 1))) return rc;
+            if ((rc = dgemm(d, g, &ma, &d->m_head, &mo, s))) return rc;
+            greedy_next_kernel<<<n, 256, 0, s>>>(d->logits_scratch, d->vocab, d->vocab_pad, d->gen_ids, Lmax, pos, eos, pad,
+                                                 d->gen_done);
+            SASVQA_CUDA_CHECK(cudaGetLastError());
+            count_launch();
+        }
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(out_ids + (size_t)b0 * Lmax, d->gen_ids, (size_t)rows_txt * sizeof(int32_t),
+                                          cudaMemcpyDeviceToDevice, s));
     }
     return 0;
 }

@@ -111,6 +111,32 @@ def vqa_loss(pixel_values: torch.Tensor, input_ids: torch.Tensor, labels: torch.
     return (loss[0], logits[:, :, :dec.vocab]) if want_logits else loss[0]
 
 
+def vqa_generate(pixel_values: torch.Tensor, input_ids: torch.Tensor, enc: FrameEncoder, dec: GitDecoder, max_length: int = 50,
+                 eos_token_id: int = 102, pad_token_id: int = 0, trim: bool = True) -> torch.Tensor:
+    """``MyGitForCausalLM.generate(pixel_values=..., input_ids=..., max_length=50)`` as the reference's evaluation calls it
+    (modeling.py:330-333): greedy search from the prompt ``input_ids`` [B, L0] (equal lengths).  Returns int64 ids
+    [B, <= max_length] on the GPU: prompt, generated tokens, pad after a sequence's eos; with ``trim`` the columns after
+    the step at which every sequence had finished are dropped, as HF stops there."""
+    px, ids = _prep(enc, pixel_values, input_ids)
+    B, K = int(px.shape[0]), int(px.shape[1])
+    L0 = int(ids.shape[1])
+    if not 1 <= L0 <= max_length:
+        raise ValueError(f"need 1 <= prompt length ({L0}) <= max_length ({max_length})")
+    out = torch.empty(B, max_length, dtype=torch.int32, device=enc.device)
+    with torch.cuda.device(enc.device):
+        _capi.check(_capi.lib().sasvqa_git_vqa_generate_f32(dec.handle, enc.handle, px.data_ptr(), B, K, ids.data_ptr(), L0,
+                                                            int(max_length), int(eos_token_id), int(pad_token_id), out.data_ptr(),
+                                                            torch.cuda.current_stream().cuda_stream),
+                    "sasvqa_git_vqa_generate_f32")
+    out = out.long()
+    if trim and B > 0:
+        gen = out[:, L0:]
+        is_eos = gen == eos_token_id
+        first = torch.where(is_eos.any(dim=1), is_eos.float().argmax(dim=1) + 1, torch.full((B,), gen.shape[1], device=out.device))
+        out = out[:, :L0 + int(first.max())]
+    return out
+
+
 def vqa_hidden(pixel_values: torch.Tensor, input_ids: torch.Tensor, enc: FrameEncoder, dec: GitDecoder, n_layers: int):
     """Inspection: (visual [B, K*197, 768], text [B, L, 768]) fp32 stream after ``n_layers`` decoder blocks."""
     px, ids = _prep(enc, pixel_values, input_ids)

@@ -136,3 +136,44 @@ def test_vqa_loss_vs_reference_expression_on_hf_logits(models, weights, golden_d
     finally:
         small.close()
     assert torch.isnan(vqa.vqa_loss(frames, ids, torch.full_like(labels, -100), enc, dec))   # nothing to predict: 0 / 0, as torch
+
+
+def test_vqa_generate_greedy_vs_fixture_and_teacher_forcing(models, weights, golden_dir):
+    """Greedy decoding (modeling.py:333) with the visual keys/values cached per block: (1) every generated token is the
+    argmax of the FULL forward on the prefix -- the cached path must agree bit for bit with sas.vqa_logits; (2) tokens
+    equal the fixture's greedy chain on HF's uncached forward, a first mismatch excused only at a top-2 margin below
+    2 x 6e-2 (after which the chains legitimately diverge)."""
+    enc, dec = models
+    g = np.load(os.path.join(golden_dir, "git_vqa_hf.npz"))
+    K = int(g["K"])
+    frames = torch.stack([vit.image_processor_224(synth.make_clip(int(c), K)) for c in g["clip_ids"]])
+    prompt = torch.from_numpy(g["gen_prompt"])
+    L0, Lmax = prompt.shape[1], g["gen_ids"].shape[1]
+    out = vqa.vqa_generate(frames, prompt, enc, dec, max_length=Lmax, trim=False).cpu()
+    assert out.shape == (2, Lmax) and torch.equal(out[:, :L0], prompt)
+    logits = sas.vqa_logits(frames, out[:, :-1], enc, dec)                    # teacher forcing on our own output
+    assert torch.equal(logits[:, L0 - 1:].argmax(dim=-1).cpu(), out[:, L0:])
+    want, margins = torch.from_numpy(g["gen_ids"]), torch.from_numpy(g["gen_margins"])
+    excused = 0
+    for b in range(2):
+        for t in range(L0, Lmax):
+            if int(out[b, t]) != int(want[b, t]):
+                assert float(margins[b, t - L0]) <= 2 * 6e-2, (b, t, out[b].tolist(), want[b].tolist())
+                excused += 1
+                break
+    assert excused <= 1
+    # eos handling: make the first generated token of sample 0 the eos id -> that sequence pads from then on, and with
+    # trim the all-finished tail is cut where HF would stop
+    eos = int(out[0, L0])
+    cut = vqa.vqa_generate(frames[:1], prompt[:1], enc, dec, max_length=Lmax, eos_token_id=eos, pad_token_id=0).cpu()
+    assert cut.shape == (1, L0 + 1) and int(cut[0, L0]) == eos
+    both = vqa.vqa_generate(frames, prompt, enc, dec, max_length=Lmax, eos_token_id=eos, pad_token_id=0, trim=False).cpu()
+    assert both[0, L0 + 1:].eq(0).all() and int(both[0, L0]) == eos
+    if eos not in out[1, L0:].tolist():
+        assert torch.equal(both[1], out[1])                                      # the other sequence is unaffected
+    # grouping into passes is invisible
+    small = vqa.GitDecoder(weights[2], max_rows=500)
+    try:
+        assert torch.equal(vqa.vqa_generate(frames, prompt, enc, small, max_length=Lmax, trim=False).cpu(), out)
+    finally:
+        small.close()

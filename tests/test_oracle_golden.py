@@ -278,5 +278,8 @@ def test_git_vqa_restatement_matches_hf_fixture(golden_dir):
     assert (logits[:, :, ::61] - torch.from_numpy(g["logits_probe"])).abs()[mask].max().item() <= 1e-4
     assert (logits[0, 3] - torch.from_numpy(g["logits_row"])).abs().max().item() <= 1e-4
     assert torch.equal(logits.topk(1, dim=-1).indices[..., 0][mask], torch.from_numpy(g["top5_idx"])[..., 0][mask])
+    # greedy decoding (modeling.py:333) against the chain of argmaxes of HF's own uncached forward
+    gen, _ = model.generate(frames, torch.from_numpy(g["gen_prompt"]), max_length=g["gen_ids"].shape[1])
+    assert torch.equal(gen, torch.from_numpy(g["gen_ids"]))
     # the reference's loss expression (modeling.py:208-215) on HF's logits
     assert abs(float(model.loss(frames, ids, torch.from_numpy(g["labels"]))) - float(g["loss"])) <= 1e-4
