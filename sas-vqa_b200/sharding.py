@@ -16,6 +16,42 @@ def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def shard_by_frames(lengths, world: int) -> list:
+    """Contiguous partition of a ragged clip list into ``world`` slices balanced by FRAME count (the encoder's cost is
+    per frame, not per clip): boundaries are placed where the running frame total crosses k * total / world, each
+    boundary at the clip edge nearest to its target.  Returns ``[(start, end)] * world`` (slices may be empty)."""
+    lens = [int(t) for t in lengths]
+    n = len(lens)
+    total = sum(lens)
+    cum = [0]
+    for t in lens:
+        cum.append(cum[-1] + t)
+    bounds = [0]
+    for k in range(1, world):
+        target = total * k / world
+        j = bounds[-1]
+        while j < n and cum[j + 1] <= target:
+            j += 1
+        if j < n and abs(cum[j + 1] - target) < abs(cum[j] - target):
+            j += 1                                      # the clip edge nearest to the target
+        bounds.append(max(j, bounds[-1]))
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def all_gather_ragged_rows(local: torch.Tensor, spans, group=None) -> torch.Tensor:
+    """all_gather of per-rank row blocks of DIFFERENT sizes: ``spans[r] = (start, end)`` rows owned by rank r."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    max_rows = max(e - s for s, e in spans)
+    pad = torch.zeros((max(max_rows, 1),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([part[: e - s] for part, (s, e) in zip(parts, spans)], dim=0)
+
+
 def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """Concatenate per-rank row blocks (sharded with ``shard_range``) into the full [n_total, ...]
     tensor on every rank.  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
@@ -56,6 +92,32 @@ def sample_mdf_sharded(make_local_clips, n_clips: int, model, K: int, W: int, gr
         idx, status = idx.cuda(), status.cuda()
     return dict(indices=all_gather_rows(idx, n_clips, group), status=all_gather_rows(status, n_clips, group),
                 local=local, shard=(start, end))
+
+
+def sample_mdf_ragged_sharded(clips, model, K: int, W: int, group=None, sampler=None) -> dict:
+    """Ragged clip list (uint8 tensors [T_i, H, W, 3] of one frame size, or a callable ``clips(i)`` plus ``lengths``
+    given as ``(lengths, loader)``) sharded by rank in contiguous slices balanced by frame count; every rank ends with
+    the full index / status tables.  ``sampler`` defaults to ``sample_mdf_ragged``."""
+    from . import sampler as S
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if isinstance(clips, tuple):
+        lengths, loader = clips
+    else:
+        lengths, loader = [int(c.shape[0]) for c in clips], (lambda i: clips[i])
+    spans = shard_by_frames(lengths, world)
+    start, end = spans[rank]
+    run = sampler if sampler is not None else S.sample_mdf_ragged
+    if end > start:
+        local = run([loader(i) for i in range(start, end)], model, K, W)
+        idx, status = local["indices"], local["status"]
+    else:
+        local = None
+        idx, status = torch.zeros(0, K, dtype=torch.int32), torch.zeros(0, dtype=torch.int32)
+    if dist.is_initialized() and world > 1 and dist.get_backend(group) == "nccl":
+        idx, status = idx.cuda(), status.cuda()
+    return dict(indices=all_gather_ragged_rows(idx, spans, group), status=all_gather_ragged_rows(status, spans, group),
+                local=local, shard=(start, end), spans=spans)
 
 
 def generate_inds_sharded(tokenizer, model, qa_samples: list, all_captions: dict, K: int, ds_rate: int = 1,

@@ -28,6 +28,12 @@ res = sharding.sample_mdf_sharded(make, n, enc, K, W)
 whole = sas.sample_mdf_batch(make(0, n), enc, K, W)
 assert torch.equal(res["indices"], whole["indices"]), (rank, res["indices"], whole["indices"])
 assert torch.equal(res["status"], whole["status"])
+# a ragged clip list, sharded by frame count, against one ragged call over the whole list on this rank
+lens = [30, 7, 52, 12, 19, 41]
+rag = [synth.make_clip(200 + i, t) for i, t in enumerate(lens)]
+rs = sharding.sample_mdf_ragged_sharded(rag, enc, K, W)
+whole_r = sas.sample_mdf_ragged([c.to(dev) for c in rag], enc, K, W)
+assert torch.equal(rs["indices"], whole_r["indices"]) and torch.equal(rs["status"], whole_r["status"]), (rank, rs["spans"])
 # the MIF step, QA list sharded by rank, against the unsharded call on this rank
 scorer = sas.CaptionScorer(synth.random_scorer_state_dict(vocab=2048), max_tokens=4096)
 tok = synth.SynthTokenizer(2048)

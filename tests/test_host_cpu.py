@@ -156,6 +156,21 @@ def test_hdf5_sampled_frames_round_trip_and_reader_pinned_on_genuine_file(tmp_pa
     assert np.array_equal(qc[0], frames[1][[3, 0, 2]].numpy()) and np.array_equal(qc[1], frames[2][[1, 1, 0]].numpy())
 
 
+def test_shard_by_frames_balances_ragged_lists():
+    import random
+    rnd = random.Random(3)
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 5, 100):
+            lens = [rnd.randint(0, 300) for _ in range(n)]
+            spans = sharding.shard_by_frames(lens, world)
+            assert len(spans) == world and spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1)) and all(s <= e for s, e in spans)
+            if n == 100:                                         # frame totals within one longest clip of the ideal share
+                loads = [sum(lens[s:e]) for s, e in spans]
+                assert max(abs(l - sum(lens) / world) for l in loads) <= max(lens)
+    assert sharding.shard_by_frames([100, 1, 1, 1, 1], 2) == [(0, 1), (1, 5)]      # by frames, not by clip count
+
+
 def test_shard_range_partitions():
     for n in (0, 1, 7, 256, 10000):
         for world in (1, 2, 3, 8):
@@ -183,6 +198,16 @@ want = torch.arange(n, dtype=torch.int32)[:, None] * 10 + torch.arange(K, dtype=
 assert torch.equal(res["indices"], want), res["indices"]
 assert torch.equal(res["status"], torch.arange(n, dtype=torch.int32) % 2)
 assert res["shard"] == sharding.shard_range(n, rank, world)
+# ---- ragged clip list sharded by frame count: tables gathered from slices of different sizes
+lens = [5, 40, 3, 3, 3, 30, 9]
+rag = [torch.full((t, 1, 1, 3), i, dtype=torch.uint8) for i, t in enumerate(lens)]     # clip i carries its id
+def fake_ragged(clips_, model, K_, W_):
+    ids = torch.tensor([int(c.flatten()[0]) if c.numel() else -1 for c in clips_], dtype=torch.int32)
+    return dict(indices=ids[:, None] * 10 + torch.arange(K_, dtype=torch.int32)[None], status=ids % 3)
+rr = sharding.sample_mdf_ragged_sharded(rag, None, K, 8, sampler=fake_ragged)
+assert rr["spans"] == sharding.shard_by_frames(lens, world) and rr["spans"][0][1] != (len(lens) + 1) // 2   # not split by count
+want_r = torch.arange(len(lens), dtype=torch.int32)[:, None] * 10 + torch.arange(K, dtype=torch.int32)[None]
+assert torch.equal(rr["indices"], want_r) and torch.equal(rr["status"], torch.arange(len(lens), dtype=torch.int32) % 3)
 # ---- MIF step sharded by QA sample: a stand-in scorer (deterministic scores from the token ids) on each rank
 from sasvqa_b200 import synth
 class FakeScorer:
