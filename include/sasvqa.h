@@ -242,7 +242,8 @@ int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const flo
  * (modeling.py:330-333; HF greedy search): prompt [B, L0] int32 (equal lengths, no padding) -> out_ids [B, max_length]
  * int32 = the prompt followed by one argmax token per step; a sequence that produced eos_token_id emits pad_token_id from
  * then on (HF stops once every sequence has finished: trim the all-pad tail).  The visual rows are run once per group
- * and their per-block keys / values cached; every step runs the text rows against the cache. */
+ * and their per-block keys / values cached; every step runs the text rows against the cache.  Synchronises `stream`
+ * every fourth step to stop a group early once all its sequences have finished. */
 int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
                                 const int32_t* prompt_ids_dev, int L0, int max_length, int eos_token_id, int pad_token_id,
                                 int32_t* out_ids_dev, void* stream);

@@ -554,7 +554,8 @@ int run_block(SasvqaGitDecoder* d, GitLayer& Ly, long long M, Attention&& attent
 // The visual rows never depend on the text (they only see each other), so they are run ONCE per group -- five full
 // blocks plus the sixth block's k|v projection -- and every block's visual keys and values are cached; a step then runs the
 // text rows alone (all max_length positions at a fixed stride: causal masking makes the not-yet-written ones harmless)
-// against the cache.  No early exit on "all finished": the step count is fixed, the tail is pad.
+// against the cache.  Every fourth step the finished flags are read back (one stream sync) and the group stops once
+// every sequence has emitted eos, as HF does; the tail is pad.
 int git_vqa_generate(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* prompt, int L0,
                      int max_length, int eos, int pad, int32_t* out_ids, cudaStream_t s) {
     SASVQA_REQUIRE(d != nullptr && enc != nullptr && B >= 0 && K >= 1, "bad arguments");
@@ -578,7 +579,7 @@ int git_vqa_generate(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frame
         SASVQA_CUDA_CHECK(cudaMalloc((void**)&d->cu_dev, (size_t)(group + 1) * sizeof(int32_t)));
         d->cu_cap = (size_t)(group + 1) * sizeof(int32_t);
     }
-    std::vector<int32_t> cu((size_t)group + 1);
+    std::vector<int32_t> cu((size_t)group + 1), done_host;
     for (int b0 = 0; b0 < B; b0 += group) {
         const int n = std::min(group, B - b0);
         const long long rows_vis = (long long)n * n_vis, rows_txt = (long long)n * Lmax;
@@ -631,6 +632,14 @@ int git_vqa_generate(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frame
                                                  d->gen_done);
             SASVQA_CUDA_CHECK(cudaGetLastError());
             count_launch();
+            // HF stops as soon as every sequence has produced eos; VQA answers are a few tokens, so look every 4th step
+            // (one small D2H + stream sync) instead of always running to max_length -- the tail is pad already
+            if ((pos - L0) % 4 == 3 && pos + 1 < Lmax) {
+                done_host.resize((size_t)n);
+                SASVQA_CUDA_CHECK(cudaMemcpyAsync(done_host.data(), d->gen_done, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                SASVQA_CUDA_CHECK(cudaStreamSynchronize(s));
+                if (std::all_of(done_host.begin(), done_host.end(), [](int32_t v) { return v != 0; })) break;
+            }
         }
         SASVQA_CUDA_CHECK(cudaMemcpyAsync(out_ids + (size_t)b0 * Lmax, d->gen_ids, (size_t)rows_txt * sizeof(int32_t),
                                           cudaMemcpyDeviceToDevice, s));

@@ -171,6 +171,10 @@ def test_vqa_generate_greedy_vs_fixture_and_teacher_forcing(models, weights, gol
     assert both[0, L0 + 1:].eq(0).all() and int(both[0, L0]) == eos
     if eos not in out[1, L0:].tolist():
         assert torch.equal(both[1], out[1])                                      # the other sequence is unaffected
+    # every sequence finished at its first step: the group stops early (checked every 4th step) and the tail is still pad
+    always = vqa.vqa_generate(frames[:1].repeat(2, 1, 1, 1, 1), prompt[:1].repeat(2, 1), enc, dec, max_length=40, eos_token_id=eos,
+                              trim=False).cpu()
+    assert always.shape == (2, 40) and always[:, L0].eq(eos).all() and always[:, L0 + 1:].eq(0).all()
     # grouping into passes is invisible
     small = vqa.GitDecoder(weights[2], max_rows=500)
     try:
