@@ -227,10 +227,10 @@ constexpr int GIT_QBLOCK = GIT_WARPS * 16;
 
 __global__ void __launch_bounds__(GIT_WARPS * 32, 2)
 attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int n_samples, int n_vis, int L,
-                     int q_blocks, int q_block0, const __nv_bfloat16* __restrict__ vis_kv, long long txt_row0) {
+                     int q_blocks, int q_row0, const __nv_bfloat16* __restrict__ vis_kv, long long txt_row0) {
     __shared__ __align__(128) uint8_t kv[2][2][64 * 128];              // [buffer][K | V][64 keys x 64 d bf16]
     const int S = n_vis + L;
-    const int qb = q_block0 + blockIdx.x % q_blocks;             // q_block0 > 0: only the blocks that hold text rows
+    const int qb = blockIdx.x % q_blocks;
     const int head = (blockIdx.x / q_blocks) % kHeads;
     const int smp = blockIdx.x / (q_blocks * kHeads);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -239,7 +239,7 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     const bool cached = vis_kv != nullptr;
     const long long vis_base = (long long)smp * n_vis, txt_base = txt_row0 + (long long)smp * L;
     auto row_of = [&](int j) -> long long { return j < n_vis ? vis_base + j : txt_base + (j - n_vis); };
-    const int q0 = qb * GIT_QBLOCK;
+    const int q0 = q_row0 + qb * GIT_QBLOCK;                     // q_row0 = n_vis: only text rows are queries
     const int q_last = min(q0 + GIT_QBLOCK, S) - 1;                      // last real query row of this block
     const int block_limit = q_last < n_vis ? n_vis : q_last + 1;         // keys any row of the block can see
     const int n_chunks = (block_limit + 63) >> 6;
@@ -330,8 +330,7 @@ attention_git_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 }  // namespace
 
-// text_only != 0: only the query blocks that contain text rows are computed (the last decoder block when nobody reads
-// the visual rows afterwards); visual rows that share a block with the first text rows are recomputed, harmlessly
+// text_only != 0: only the text rows are queries (the last decoder block when nobody reads the visual rows afterwards)
 // vis_kv != nullptr: incremental decoding -- qkv / out are the text rows only ([n * L, .], sample-major), the visual keys
 // and values are read from the cache [n * n_vis, 1536] (k | v) of this layer; only text query blocks run
 int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, int text_only,
@@ -340,14 +339,15 @@ int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_sam
     if (vis_kv != nullptr) text_only = 1;
     SASVQA_REQUIRE(n_vis >= 1 && L >= 0, "the visual prefix must hold at least one token");
     SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
-    const int all_blocks = (n_vis + L + GIT_QBLOCK - 1) / GIT_QBLOCK;
-    const int q_block0 = text_only ? n_vis / GIT_QBLOCK : 0;
-    const int q_blocks = all_blocks - q_block0;
+    // text_only: query blocks are laid over the text rows alone (first block starts at row n_vis), so no warp spends its
+    // chunks on visual rows nobody reads
+    const int q_row0 = text_only ? n_vis : 0;
+    const int q_blocks = (n_vis + L - q_row0 + GIT_QBLOCK - 1) / GIT_QBLOCK;
     if (q_blocks <= 0) return 0;                                  // text_only with L == 0
     const long long grid = (long long)n_samples * kHeads * q_blocks;
     SASVQA_REQUIRE(grid < 2147483647LL, "too many attention blocks for one launch");
     const long long txt_row0 = vis_kv != nullptr ? 0 : (long long)n_samples * n_vis;
-    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks, q_block0, vis_kv,
+    attention_git_kernel<<<(unsigned)grid, GIT_WARPS * 32, 0, s>>>(qkv, out, n_samples, n_vis, L, q_blocks, q_row0, vis_kv,
                                                                    txt_row0);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
