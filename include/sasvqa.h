@@ -247,7 +247,7 @@ int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const flo
 int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
                                 const int32_t* prompt_ids_dev, int L0, int max_length, int eos_token_id, int pad_token_id,
                                 int32_t* out_ids_dev, void* stream);
-/* inspection: fp32 stream [B*K*197 + B*L, 768] after `n_layers` blocks (all visual rows first, then all text rows);
+/* inspection: fp32 stream [B*K*197 + B*L, 768] after `n_layers` >= 0 blocks (all visual rows first, then all text rows);
  * the call must fit one pass */
 int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
                               const int32_t* input_ids_dev, int L, int n_layers, float* hidden_dev, void* stream);

@@ -217,18 +217,19 @@ int sasvqa_git_decoder_vocab_padded(const SasvqaGitDecoder* dec) { return git_de
 int sasvqa_git_vqa_logits_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
                               int L, float* logits, void* stream) {
     SASVQA_REQUIRE(B == 0 || logits != nullptr, "null logits");
-    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits, 1 << 30, nullptr, nullptr, nullptr, S(stream));
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits, -1, nullptr, nullptr, nullptr, S(stream));
 }
 int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
                               int L, int n_layers, float* hidden, void* stream) {
     SASVQA_REQUIRE(B == 0 || hidden != nullptr, "null hidden");
+    SASVQA_REQUIRE(n_layers >= 0, "bad layer count");
     return git_vqa_logits(dec, enc, frames, B, K, ids, L, nullptr, n_layers, hidden, nullptr, nullptr, S(stream));
 }
 int sasvqa_git_vqa_loss_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* ids,
                             const int32_t* labels, int L, float* loss, float* logits_or_null, void* stream) {
     SASVQA_REQUIRE(loss != nullptr && labels != nullptr, "null loss / labels");
     SASVQA_REQUIRE(B >= 1, "the loss of an empty batch is undefined");
-    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits_or_null, 1 << 30, nullptr, labels, loss, S(stream));
+    return git_vqa_logits(dec, enc, frames, B, K, ids, L, logits_or_null, -1, nullptr, labels, loss, S(stream));
 }
 int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames, int B, int K, const int32_t* prompt,
                                 int L0, int max_length, int eos_token_id, int pad_token_id, int32_t* out_ids, void* stream) {

@@ -405,7 +405,7 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
                    cudaStream_t s) {
     SASVQA_REQUIRE(d != nullptr && enc != nullptr && B >= 0 && K >= 1, "bad arguments");
     SASVQA_REQUIRE(L >= 1 && L <= kGitMaxPos, "text length must be in [1, 1024] (GIT position table)");
-    if (n_layers == 1 << 30) n_layers = d->n_layers;            // "all of them" (the logits entry point)
+    if (n_layers < 0) n_layers = d->n_layers;                   // -1 = all of them (the logits / loss entry points)
     SASVQA_REQUIRE(n_layers >= 0 && n_layers <= d->n_layers, "bad layer count");
     if (B == 0) return 0;
     const bool want_loss = loss_or_null != nullptr;
