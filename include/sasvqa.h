@@ -266,13 +266,15 @@ int sasvqa_profile_read(SasvqaEncoder* enc, double* ms_out, int64_t* scopes_out,
 
 /* ---- test hooks (not on the product path) ---------------------------------------------------
  * One encoder GEMM with a fused epilogue (mode = 0 bias->bf16, 1 bias+quick_gelu->bf16,
- * 2 bias+residual in place fp32, 3 patch-embed scatter + position embedding, 4 bias+erf-gelu->bf16).  use_simt != 0 runs
- * the CUDA-core check kernel instead of the tcgen05 kernel. */
+ * 2 bias+residual in place fp32, 3 patch-embed scatter + position embedding, 4 bias+erf-gelu->bf16) on the product's
+ * tcgen05 kernel.  The library has ONE backend per operation and no runtime switch: the CUDA-core / mma.sync check
+ * kernels the parity tests compare against live in a separate test-only library (libsasvqa_b200_test.so,
+ * csrc/check/: sasvqa_check_gemm_simt, sasvqa_check_attention_mma). */
 int sasvqa_test_gemm(const uint16_t* a_bf16_dev, const uint16_t* b_bf16_dev, int M, int N, int K, int mode,
-                     const float* bias_or_pos_dev, uint16_t* out_bf16_dev, float* out_f32_dev, int use_simt,
-                     void* stream);
-/* impl: 0 = tcgen05 kernel (product path), 1 = mma.sync check kernel */
-int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* out_bf16_dev, int impl, void* stream);
+                     const float* bias_or_pos_dev, uint16_t* out_bf16_dev, float* out_f32_dev, void* stream);
+/* the encoder's per-frame attention (tcgen05 kernel); trace_variant > 0 selects an instrumented timing variant of
+ * the same kernel (tools/att_trace.py), 0 = the product launch */
+int sasvqa_test_attention(const uint16_t* qkv_bf16_dev, int n_frames, uint16_t* out_bf16_dev, int trace_variant, void* stream);
 int sasvqa_test_layernorm(const float* x_dev, int rows, const float* gamma_dev, const float* beta_dev,
                           uint16_t* out_bf16_dev, void* stream);
 /* variable-length attention of the scorer: packed qkv [M, 2304] bf16, cu_seqlens_dev [n_seqs + 1] -> out [M, 768] */

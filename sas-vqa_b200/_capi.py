@@ -65,12 +65,21 @@ SIGNATURES = {
     "sasvqa_launch_count": (c_int64, []),
     "sasvqa_profile_enable": (c_int, [_p, c_int]),
     "sasvqa_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
-    "sasvqa_test_gemm": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, c_int, _p]),
+    "sasvqa_test_gemm": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p]),
     "sasvqa_test_attention": (c_int, [_p, c_int, _p, c_int, _p]),
     "sasvqa_test_layernorm": (c_int, [_p, c_int, _p, _p, _p, _p]),
 }
 
+# test-only library (csrc/check/): CUDA-core GEMM and mma.sync attention check kernels, never loaded by the product path
+TEST_LIB_PATH = os.path.join(HERE, "libsasvqa_b200_test.so")
+TEST_SIGNATURES = {
+    "sasvqa_check_last_error": (c_char_p, []),
+    "sasvqa_check_gemm_simt": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p]),
+    "sasvqa_check_attention_mma": (c_int, [_p, c_int, _p, _p]),
+}
+
 _lib = None
+_test_lib = None
 
 
 class SasvqaError(RuntimeError):
@@ -92,6 +101,27 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def test_lib() -> ctypes.CDLL:
+    """The check kernels the parity tests compare the product kernels against (tests and tools only)."""
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise SasvqaError(f"{TEST_LIB_PATH} is missing: run `python __graft_entry__.py`")
+        handle = ctypes.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in TEST_SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _test_lib = handle
+    return _test_lib
+
+
+def check_test(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = test_lib().sasvqa_check_last_error()
+        raise SasvqaError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
 
 
 def check(rc: int, what: str) -> None:

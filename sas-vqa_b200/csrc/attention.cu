@@ -1,219 +1,16 @@
-// Per-frame multi-head self-attention of the ViT encoder: 197 tokens, 12 heads x 64.
-// softmax(Q K^T / 8) V with fp32 softmax statistics (HF eager_attention_forward,
-// transformers modeling_git.py:556-575, reached from the reference at
-// src/preprocessing/datautils/utils.py:40).
-//
-// Input  qkv [n*197, 2304] bf16 (q | k | v, each 12 heads x 64) from the fused projection GEMM.
-// Output out [n*197, 768] bf16 (heads concatenated), the A operand of the out_proj GEMM.
-//
-// One CTA per (frame, head): K and V (197x64 bf16 each, XOR-swizzled 16-byte chunks) are staged
-// in shared memory with cp.async, 7 warps each own 16-query tiles (13 tiles) and run a
-// flash-style online softmax over key chunks 64/64/64/16 on bf16 mma.sync.m16n8k16 with fp32
-// accumulators.  (~4 % of the encoder's FLOPs; a tcgen05 version is listed in DESIGN.md "next".)
+// Small attention kernels on bf16 mma.sync.m16n8k16 with fp32 softmax statistics:
+//  * attention_git_kernel     -- the GIT decoder's attention over [visual tokens | text] for the TEXT-ROW passes (sixth
+//                                block of the forward, greedy decoding steps); the full passes run on tcgen05
+//  * attention_short_kernel / attention_varlen_kernel -- the MIF caption cross-encoder's (question, caption) pairs
+//                                (~20 tokens; a tcgen05 instruction needs 128 query rows, six times a pair's length)
+// The encoder's per-frame attention is attention_tcgen05.cu.
 #include <algorithm>
 
-#include "common.cuh"
+#include "attention_mma.cuh"
 
 namespace sasvqa {
 
 namespace {
-
-constexpr int ATT_WARPS = 7;
-constexpr int ATT_THREADS = ATT_WARPS * 32;
-constexpr int KEYS_PAD = 208;                       // 197 rounded up to 16
-constexpr int Q_TILES = (kTokens + 15) / 16;        // 13
-constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
-
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                 : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                 : "r"(addr));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {          // one MUFU op, no range fix-ups (arguments are <= 0)
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// byte offset of 16-byte chunk `c` (0..7) of row `r` in a [rows][64] bf16 tile, XOR-swizzled so
-// that ldmatrix (8 rows x 16 B) is bank-conflict free
-__device__ __forceinline__ uint32_t tile_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
-
-// one key chunk of NT*8 keys starting at key0: S = Q K^T, online softmax update, O += P V
-template <int NT>
-__device__ __forceinline__ void attend_chunk(const uint32_t (&qf)[4][4], uint32_t k_smem, uint32_t v_smem, int key0,
-                                             int lane, float (&m)[2], float (&l)[2], float (&o)[8][4],
-                                             int n_valid = kTokens, int n_valid_hi = -1) {
-    // n_valid: keys [0, n_valid) are visible to row g of the tile; n_valid_hi (default: the same) to row g + 8
-    if (n_valid_hi < 0) n_valid_hi = n_valid;
-    float s[NT][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-    // ---- S = Q K^T : B fragments straight from K rows (key-major, d contiguous)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const int key = key0 + nt * 8 + (lane & 7);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {          // d 0..31, d 32..63
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4(k_smem + tile_off(key, half * 4 + (lane >> 3)), b0, b1, b2, b3);
-            mma_bf16(s[nt], qf[half * 2 + 0], b0, b1);
-            mma_bf16(s[nt], qf[half * 2 + 1], b2, b3);
-        }
-    }
-    // ---- mask invisible keys (only chunks that reach past a row's limit pay for it), chunk row maxima of the RAW
-    // scores (rows g and g+8); the 1/8 * log2(e) scale is folded into the exponent's FFMA below
-    float cmax[2] = {-INFINITY, -INFINITY};
-    if (key0 + NT * 8 > min(n_valid, n_valid_hi)) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int kcol = key0 + nt * 8 + 2 * (lane & 3);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool valid = (kcol + (e & 1)) < ((e >> 1) ? n_valid_hi : n_valid);
-                s[nt][e] = valid ? s[nt][e] : -INFINITY;
-            }
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        cmax[0] = fmaxf(cmax[0], fmaxf(s[nt][0], s[nt][1]));
-        cmax[1] = fmaxf(cmax[1], fmaxf(s[nt][2], s[nt][3]));
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        cmax[r] = fmaxf(cmax[r], __shfl_xor_sync(0xffffffffu, cmax[r], 1));
-        cmax[r] = fmaxf(cmax[r], __shfl_xor_sync(0xffffffffu, cmax[r], 2));
-    }
-    float alpha[2], mnew[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        mnew[r] = fmaxf(m[r], cmax[r] * kScaleLog2);  // finite: a row's FIRST chunk always holds >= 1 visible key
-        alpha[r] = ex2_approx(m[r] - mnew[r]);        // first chunk: exp2(-inf) = 0
-        m[r] = mnew[r];
-        l[r] *= alpha[r];
-    }
-    // rescale the accumulator only when some row's maximum moved (alpha == 1 exactly otherwise: a bit-identical skip;
-    // after the first few chunks of a long key range that is most of the time)
-    if (__any_sync(0xffffffffu, alpha[0] != 1.0f || alpha[1] != 1.0f)) {
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-            o[dt][0] *= alpha[0];
-            o[dt][1] *= alpha[0];
-            o[dt][2] *= alpha[1];
-            o[dt][3] *= alpha[1];
-        }
-    }
-    // ---- P = exp2(S * scale - m), packed to bf16 A fragments; O += P V
-#pragma unroll
-    for (int kk = 0; kk < NT / 2; ++kk) {
-        uint32_t pa[4];
-        float p[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                p[j][e] = ex2_approx(fmaf(s[2 * kk + j][e], kScaleLog2, -mnew[e >> 1]));   // masked: fma(-inf) = -inf -> 0
-                l[e >> 1] += p[j][e];
-            }
-        }
-        pa[0] = pack_bf16x2(p[0][0], p[0][1]);
-        pa[1] = pack_bf16x2(p[0][2], p[0][3]);
-        pa[2] = pack_bf16x2(p[1][0], p[1][1]);
-        pa[3] = pack_bf16x2(p[1][2], p[1][3]);
-        const int vrow = key0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-#pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {                // two 8-wide d tiles per ldmatrix.x4
-            uint32_t b0, b1, b2, b3;
-            ldsm_x4_trans(v_smem + tile_off(vrow, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
-            mma_bf16(o[dp * 2 + 0], pa, b0, b1);
-            mma_bf16(o[dp * 2 + 1], pa, b2, b3);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __align__(128) uint8_t att_smem[];
-    uint8_t* k_tile = att_smem;
-    uint8_t* v_tile = att_smem + KEYS_PAD * 128;
-    const int head = blockIdx.x % kHeads;
-    const long long frame = blockIdx.x / kHeads;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const __nv_bfloat16* base = qkv + frame * kTokens * (long long)kQkv + head * kHeadDim;
-    const uint32_t k_smem = (uint32_t)__cvta_generic_to_shared(k_tile);
-    const uint32_t v_smem = (uint32_t)__cvta_generic_to_shared(v_tile);
-
-    // ---- stage K and V (zero the padded rows: P is 0 there but 0 * garbage could be NaN)
-    for (int i = threadIdx.x; i < KEYS_PAD * 8; i += ATT_THREADS) {
-        const int r = i >> 3, c = i & 7;
-        if (r < kTokens) {
-            const __nv_bfloat16* src = base + (long long)r * kQkv + c * 8;
-            cp_async16(k_smem + tile_off(r, c), src + kHidden);
-            cp_async16(v_smem + tile_off(r, c), src + 2 * kHidden);
-        } else {
-            *reinterpret_cast<uint4*>(k_tile + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(v_tile + tile_off(r, c)) = make_uint4(0, 0, 0, 0);
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
-    const int g = lane >> 2, t = lane & 3;
-    for (int qt = warp; qt < Q_TILES; qt += ATT_WARPS) {
-        const int row0 = qt * 16 + g, row1 = row0 + 8;
-        const int r0c = min(row0, kTokens - 1), r1c = min(row1, kTokens - 1);
-        // ---- Q fragments (A operand, 16 queries x 64 d) straight from global
-        uint32_t qf[4][4];
-        const __nv_bfloat16* q0 = base + (long long)r0c * kQkv + 2 * t;
-        const __nv_bfloat16* q1 = base + (long long)r1c * kQkv + 2 * t;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            qf[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 16 * ks));
-            qf[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 16 * ks));
-            qf[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(q0 + 16 * ks + 8));
-            qf[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + 16 * ks + 8));
-        }
-        float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, o[8][4];
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
-
-        attend_chunk<8>(qf, k_smem, v_smem, 0, lane, m, l, o);
-        attend_chunk<8>(qf, k_smem, v_smem, 64, lane, m, l, o);
-        attend_chunk<8>(qf, k_smem, v_smem, 128, lane, m, l, o);
-        attend_chunk<2>(qf, k_smem, v_smem, 192, lane, m, l, o);
-
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
-            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
-        }
-        const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
-        __nv_bfloat16* o0 = out + (frame * kTokens + row0) * (long long)kHidden + head * kHeadDim + 2 * t;
-        __nv_bfloat16* o1 = out + (frame * kTokens + row1) * (long long)kHidden + head * kHeadDim + 2 * t;
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt) {
-            if (row0 < kTokens) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
-            if (row1 < kTokens) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
-        }
-    }
-}
 
 // ---- attention of the downstream GIT decoder over [visual tokens | text] (HF GitSelfAttention, modeling_git.py:202-280,
 // with the mask MyGitModel.forward builds, src/modeling/modeling.py:116-140): a visual row sees the n_vis visual rows,
@@ -532,18 +329,6 @@ int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const 
     static SmemAttrCache smem_attr;
     if (int rc = smem_attr.ensure(attention_varlen_kernel, smem)) return rc;
     attention_varlen_kernel<<<n_seqs * kHeads, VAR_WARPS * 32, smem, s>>>(qkv, out, cu_seqlens_dev, row_base);
-    SASVQA_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-    return 0;
-}
-
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, cudaStream_t s) {
-    if (n_frames == 0) return 0;
-    SASVQA_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0, "unaligned buffers");
-    constexpr int smem = 2 * KEYS_PAD * 128;   // 53 248 B: above the 48 KiB static limit
-    static SmemAttrCache smem_attr;
-    if (int rc = smem_attr.ensure(attention_kernel, smem)) return rc;
-    attention_kernel<<<n_frames * kHeads, ATT_THREADS, smem, s>>>(qkv, out);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

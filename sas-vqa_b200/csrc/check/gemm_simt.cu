@@ -1,7 +1,7 @@
 // CUDA-core check GEMM with the same fused epilogues as gemm_tcgen05.cu.
 // NOT on the product path: it exists so tests (and SASVQA_DEBUG_SIMT_GEMM=1 when bisecting a
 // failure on the GPU box) can tell a tcgen05/TMA descriptor bug from a bug in the other kernels.
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace sasvqa {
 

@@ -65,6 +65,27 @@ struct SmemAttrCache {
     }
 };
 
+// A handle owns ONE workspace, but its entry points may be called on different streams (the caller's stream for the
+// device-pointer entries, the handle's own copy / compute streams for the host-buffer pipelines).  Every entry opens a
+// StreamOrder scope: its stream first waits for the last work any earlier entry queued on the workspace, and the scope's
+// end marks the new tail -- so "a handle serialises its own work" (include/sasvqa.h) holds across streams too.
+struct WorkspaceOrder {
+    cudaEvent_t tail = nullptr;     // created with the handle (cudaEventDisableTiming)
+    bool armed = false;
+};
+struct StreamOrder {
+    WorkspaceOrder* o;
+    cudaStream_t s;
+    StreamOrder(WorkspaceOrder* o_, cudaStream_t s_) : o(o_), s(s_) {
+        if (o && o->tail && o->armed) cudaStreamWaitEvent(s, o->tail, 0);
+    }
+    ~StreamOrder() {
+        if (o && o->tail && cudaEventRecord(o->tail, s) == cudaSuccess) o->armed = true;
+    }
+    StreamOrder(const StreamOrder&) = delete;
+    StreamOrder& operator=(const StreamOrder&) = delete;
+};
+
 // ---- epilogue modes of the encoder GEMM
 enum GemmEpilogue : int {
     EPI_BIAS_BF16 = 0,        // out_bf16 = acc + bias                         (fused q|k|v projection)
@@ -89,7 +110,6 @@ struct GemmArgs {
 int launch_gemm_tcgen05(const GemmArgs& g, const CUtensorMap* map_a, const CUtensorMap* map_b,
                         const CUtensorMap* map_out, int num_sms, cudaStream_t stream);
 int make_tensor_map_out(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, int is_f32);
-int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream);
 int make_tensor_map_bf16_kmajor(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 int launch_resize_crop_u8(const uint8_t* frames_hwc, long long n_src, int H, int W, const int32_t* frame_map,
@@ -105,7 +125,6 @@ int launch_layernorm_f32(const float* x, float* out, long long rows, const float
                          cudaStream_t s);
 int launch_pool_norm(const float* x, int n_frames, const float* gamma, const float* beta, float* feats,
                      cudaStream_t s);
-int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_frames, cudaStream_t s);   // mma.sync check kernel
 int make_attention_maps(CUtensorMap* map_q, CUtensorMap* map_kv, CUtensorMap* map_out, const void* qkv, const void* out,
                         uint64_t rows);
 int launch_attention_tcgen05(const CUtensorMap* map_q, const CUtensorMap* map_kv, const CUtensorMap* map_out,

@@ -68,7 +68,6 @@ struct SasvqaEncoder {
     int device = 0;
     int num_sms = 148;
     int chunk_frames = 0;
-    bool use_simt = false;           // SASVQA_DEBUG_SIMT_GEMM=1: bisecting aid, never set in production
     // weights (one arena each for bf16 matrices and fp32 vectors)
     __nv_bfloat16* arena_bf16 = nullptr;
     float* arena_f32 = nullptr;
@@ -86,7 +85,6 @@ struct SasvqaEncoder {
     __nv_bfloat16* big = nullptr;     // [chunk*197, 3072] qkv (as [.,2304]) / fc1 output / patch matrix (as [chunk*196,768])
     CUtensorMap m_h, m_big_fc, m_big_patch;       // A-operand views
     CUtensorMap m_att_q, m_att_kv, m_att_out;     // attention operand views of big as [., 2304]; output view of h
-    bool use_mma_attention = false;               // SASVQA_DEBUG_MMA_ATTENTION=1: legacy mma.sync kernel (bisecting aid)
     CUtensorMap m_out_qkv, m_out_fc1, m_out_x;    // TMA-store views of big ([.,2304] / [.,3072]) and x
     // scratch for the whole-path entry points (grown on demand)
     float* feats = nullptr;
@@ -111,6 +109,7 @@ struct SasvqaEncoder {
     int32_t* idx_stage[2] = {nullptr, nullptr};
     size_t idx_stage_cap[2] = {0, 0};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    WorkspaceOrder order;             // serialises the entry points across the streams they are called on
     // optional per-stage timing
     bool profile = false;
     std::vector<ProfRec> prof;
@@ -154,7 +153,6 @@ struct Scope {
 int gemm(SasvqaEncoder* e, int kind, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb,
          const CUtensorMap* mo, cudaStream_t s) {
     Scope sc(e, kind, s);
-    if (e->use_simt) return launch_gemm_simt(g, s);
     return launch_gemm_tcgen05(g, ma, mb, mo, e->num_sms, s);
 }
 
@@ -184,8 +182,7 @@ int encode_chunk(SasvqaEncoder* e, const __nv_bfloat16* patches, const CUtensorM
         if ((rc = gemm(e, PK_GEMM_QKV, g, &e->m_h, &L.m_qkv, &e->m_out_qkv, s))) return rc;
         {
             Scope sc(e, PK_ATTENTION, s);
-            if (e->use_mma_attention) rc = launch_attention(e->big, e->h, n, s);
-            else rc = launch_attention_tcgen05(&e->m_att_q, &e->m_att_kv, &e->m_att_out, e->h, n, e->num_sms, s);
+            rc = launch_attention_tcgen05(&e->m_att_q, &e->m_att_kv, &e->m_att_out, e->h, n, e->num_sms, s);
             if (rc) return rc;
         }
         g = GemmArgs{};
@@ -238,10 +235,6 @@ int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames
     }
     e->num_sms = prop.multiProcessorCount;
     e->chunk_frames = chunk_frames;
-    const char* dbg = getenv("SASVQA_DEBUG_SIMT_GEMM");
-    e->use_simt = dbg != nullptr && dbg[0] == '1';
-    dbg = getenv("SASVQA_DEBUG_MMA_ATTENTION");
-    e->use_mma_attention = dbg != nullptr && dbg[0] == '1';
 
     // ---- upload the fp32 state dict once, carve bf16 matrices / fp32 vectors out of it on device
     float* raw = nullptr;
@@ -345,6 +338,7 @@ int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames
     TRYCUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));
     TRYCUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&e->order.tail, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         TRYCUDA(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
         TRYCUDA(cudaEventCreateWithFlags(&e->ev_comp[i], cudaEventDisableTiming));
@@ -397,6 +391,7 @@ void encoder_destroy(SasvqaEncoder* e) {
         if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
     }
+    if (e->order.tail) cudaEventDestroy(e->order.tail);
     for (const ProfRec& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
@@ -408,6 +403,7 @@ void encoder_destroy(SasvqaEncoder* e) {
 // patches (caller memory) -> feats, any n
 int encoder_fwd(SasvqaEncoder* e, const __nv_bfloat16* patches, int n_frames, float* feats, cudaStream_t s) {
     SASVQA_REQUIRE(e != nullptr && n_frames >= 0, "bad arguments");
+    StreamOrder order(&e->order, s);
     for (int f0 = 0; f0 < n_frames; f0 += e->chunk_frames) {
         const int n = std::min(e->chunk_frames, n_frames - f0);
         const __nv_bfloat16* p = patches + (size_t)f0 * kPatches * kHidden;
@@ -427,6 +423,7 @@ int encoder_fwd_hidden(SasvqaEncoder* e, const __nv_bfloat16* patches, int n_fra
                        cudaStream_t s) {
     SASVQA_REQUIRE(e != nullptr && n_frames > 0 && n_frames <= e->chunk_frames, "n_frames must be in (0, chunk_frames]");
     SASVQA_REQUIRE(n_layers >= 0 && n_layers <= kLayers, "n_layers out of range");
+    StreamOrder order(&e->order, s);
     CUtensorMap mp;
     int rc = make_tensor_map_bf16_kmajor(&mp, patches, (uint64_t)n_frames * kPatches, kHidden, 128);
     if (rc) return rc;
@@ -508,6 +505,7 @@ int visual_tokens(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int n_f
     SASVQA_REQUIRE(e != nullptr && n_frames >= 0, "bad arguments");
     SASVQA_REQUIRE(n_frames == 0 || ((u8 != nullptr || f32 != nullptr) && tokens != nullptr), "null argument");
     SASVQA_REQUIRE(!project || e->w_proj != nullptr, "no visual projection loaded (sasvqa_encoder_set_projection)");
+    StreamOrder order(&e->order, s);
     for (int f0 = 0; f0 < n_frames; f0 += e->chunk_frames) {
         const int n = std::min(e->chunk_frames, n_frames - f0);
         const long long rows = (long long)n * kTokens;
@@ -535,8 +533,7 @@ int visual_tokens(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int n_f
             GemmArgs g{};
             g.A = e->h; g.B = e->w_proj; g.M = (int)rows; g.N = kHidden; g.K = kHidden;
             g.epilogue = EPI_BIAS_RESID_F32; g.bias = e->proj_vec; g.out_f32 = e->x;
-            if (e->use_simt) rc = launch_gemm_simt(g, s);
-            else rc = launch_gemm_tcgen05(g, &e->m_h, &e->m_proj, &e->m_out_x, e->num_sms, s);
+            rc = launch_gemm_tcgen05(g, &e->m_h, &e->m_proj, &e->m_out_x, e->num_sms, s);
             if (rc) return rc;
             if ((rc = launch_layernorm_f32(e->x, out, rows, e->proj_vec + kHidden, e->proj_vec + 2 * kHidden, s))) return rc;
         }
@@ -587,6 +584,7 @@ int mdf_sample_ragged_device(SasvqaEncoder* e, const uint8_t* u8, const float* f
     SASVQA_REQUIRE(W >= -1, "W must be >= 0, or -1 for the adaptive width T / 20");
     if (B == 0) return 0;
     SASVQA_REQUIRE(off_host[0] == 0, "clip offsets must start at 0");
+    StreamOrder order(&e->order, s);
     int t_max = 0;
     for (int b = 0; b < B; ++b) {
         SASVQA_REQUIRE(off_host[b + 1] >= off_host[b], "clip offsets must not decrease");
@@ -634,6 +632,7 @@ int mdf_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
     SASVQA_REQUIRE(u8 != nullptr || (H == kImg && Wd == kImg), "fp32 frames are already processed: they must be 224x224");
     SASVQA_REQUIRE(W >= -1, "W must be >= 0, or -1 for the adaptive width T / 20");
     if (B == 0) return 0;
+    StreamOrder order(&e->order, s);
     if (W == -1) W = T / 20;                                    // utils.py:32-33
     if (T == 0) {                                               // utils.py:50-52: zero frames, 'Zeros'
         fill_i32_kernel<<<(B + 255) / 256, 256, 0, s>>>(status, SASVQA_STATUS_EMPTY, B);
@@ -677,6 +676,7 @@ int mif_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
     SASVQA_REQUIRE(u8 != nullptr || (H == kImg && Wd == kImg), "fp32 frames are already processed: they must be 224x224");
     SASVQA_REQUIRE(K <= (T + ds_rate - 1) / ds_rate, "selected index k out of range");
     if (B == 0) return 0;
+    StreamOrder order(&e->order, s);
     int rc;
     const size_t nf = (size_t)B * T;
     float* feats = feats_out;
@@ -699,6 +699,19 @@ int mif_sample_device(SasvqaEncoder* e, const uint8_t* u8, const float* f32, int
         if ((rc = launch_topk_strided(scores, B, T, ds_rate, K, idx, nullptr, s))) return rc;
     }
     return sampled ? gather_picks(e, u8, f32, B, T, H, Wd, K, idx, sampled, s) : 0;
+}
+
+// waits for everything the host-buffer pipelines queued; returns the first CUDA error (reported, not thrown)
+static int drain_pipeline(SasvqaEncoder* e) {
+    const cudaError_t a = cudaStreamSynchronize(e->d2h_stream);
+    const cudaError_t b = cudaStreamSynchronize(e->compute_stream);
+    const cudaError_t c = cudaStreamSynchronize(e->h2d_stream);
+    const cudaError_t bad = a != cudaSuccess ? a : (b != cudaSuccess ? b : c);
+    if (bad != cudaSuccess) {
+        set_last_error(std::string("host-buffer pipeline: ") + cudaGetErrorString(bad));
+        return SASVQA_ERR_CUDA;
+    }
+    return 0;
 }
 
 // Host-buffer pipeline: groups of whole clips; H2D (h2d_stream), compute (compute_stream) and
@@ -727,7 +740,7 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
             return rc;
     }
     const int n_groups = (B + group - 1) / group;
-    for (int gi = 0; gi < n_groups; ++gi) {
+    auto run_group = [&](int gi) -> int {
         const int slot = gi & 1;
         const int b0 = gi * group, nb = std::min(group, B - b0);
         // stage[slot] is free once group gi-2 has finished computing (its gather reads the frames)
@@ -741,9 +754,9 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
         int32_t* d_idx = e->idx_stage[slot];
         int32_t* d_status = d_idx + (size_t)group * K;
         float* d_out = sampled_host ? e->out_stage[slot] : nullptr;
-        if ((rc = mdf_sample_device(e, e->stage[slot], nullptr, nb, T, H, Wd, K, W, d_idx, d_status, nullptr, nullptr, d_out,
-                                    e->compute_stream)))
-            return rc;
+        if (int rc2 = mdf_sample_device(e, e->stage[slot], nullptr, nb, T, H, Wd, K, W, d_idx, d_status, nullptr, nullptr, d_out,
+                                        e->compute_stream))
+            return rc2;
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_comp[slot], e->compute_stream));
         SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->ev_comp[slot], 0));
         SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host + (size_t)b0 * K, d_idx, (size_t)nb * K * sizeof(int32_t),
@@ -755,11 +768,12 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
                                               (size_t)nb * K * kFrameElems * sizeof(float), cudaMemcpyDeviceToHost,
                                               e->d2h_stream));
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_out[slot], e->d2h_stream));
-    }
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->compute_stream));
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->h2d_stream));
-    return 0;
+        return 0;
+    };
+    rc = 0;
+    for (int gi = 0; gi < n_groups && rc == 0; ++gi) rc = run_group(gi);
+    const int rc_drain = drain_pipeline(e);     // also on failure: no copy to / from the caller's buffers stays in flight
+    return rc ? rc : rc_drain;
 }
 
 // Host-buffer pipeline for ragged batches: consecutive whole clips are grouped up to chunk_frames frames (a longer clip
@@ -796,7 +810,7 @@ int mdf_sample_ragged_host(SasvqaEncoder* e, const uint8_t* frames, int B, const
     }
     std::vector<int32_t> off_g;
     const int n_groups = (int)g_begin.size() - 1;
-    for (int gi = 0; gi < n_groups; ++gi) {
+    auto run_group = [&](int gi) -> int {
         const int slot = gi & 1;
         const int b0 = g_begin[gi], nb = g_begin[gi + 1] - b0;
         const long long f0 = off_host[b0], nf = off_host[b0 + nb] - f0;
@@ -812,9 +826,9 @@ int mdf_sample_ragged_host(SasvqaEncoder* e, const uint8_t* frames, int B, const
         int32_t* d_idx = e->idx_stage[slot];
         int32_t* d_status = d_idx + (size_t)max_clips * K;
         float* d_out = sampled_host ? e->out_stage[slot] : nullptr;
-        if ((rc = mdf_sample_ragged_device(e, e->stage[slot], nullptr, nb, off_g.data(), H, Wd, K, W, d_idx, d_status, nullptr,
-                                           nullptr, d_out, e->compute_stream)))
-            return rc;
+        if (int rc2 = mdf_sample_ragged_device(e, e->stage[slot], nullptr, nb, off_g.data(), H, Wd, K, W, d_idx, d_status,
+                                               nullptr, nullptr, d_out, e->compute_stream))
+            return rc2;
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_comp[slot], e->compute_stream));
         SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->ev_comp[slot], 0));
         SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host + (size_t)b0 * K, d_idx, (size_t)nb * K * sizeof(int32_t),
@@ -826,11 +840,12 @@ int mdf_sample_ragged_host(SasvqaEncoder* e, const uint8_t* frames, int B, const
                                               (size_t)nb * K * kFrameElems * sizeof(float), cudaMemcpyDeviceToHost,
                                               e->d2h_stream));
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_out[slot], e->d2h_stream));
-    }
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->d2h_stream));
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->compute_stream));
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->h2d_stream));
-    return 0;
+        return 0;
+    };
+    rc = 0;
+    for (int gi = 0; gi < n_groups && rc == 0; ++gi) rc = run_group(gi);
+    const int rc_drain = drain_pipeline(e);
+    return rc ? rc : rc_drain;
 }
 
 }  // namespace sasvqa

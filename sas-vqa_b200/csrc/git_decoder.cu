@@ -197,7 +197,7 @@ struct SasvqaGitDecoder {
     int device = 0;
     int num_sms = 148;
     int vocab = 0, vocab_pad = 0, n_layers = 0, max_rows = 0;
-    bool use_simt = false;
+    WorkspaceOrder order;              // serialises the entry points across the streams they are called on
     __nv_bfloat16* arena_bf16 = nullptr;
     float* arena_f32 = nullptr;
     float *word = nullptr, *pos = nullptr, *emb_g = nullptr, *emb_b = nullptr, *zero_row = nullptr;
@@ -245,7 +245,6 @@ int dgrow(void** p, size_t* cap, size_t need) {
 
 int dgemm(SasvqaGitDecoder* d, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, const CUtensorMap* mo,
           cudaStream_t s) {
-    if (d->use_simt) return launch_gemm_simt(g, s);
     return launch_gemm_tcgen05(g, ma, mb, mo, d->num_sms, s);
 }
 
@@ -263,6 +262,7 @@ void git_decoder_destroy(SasvqaGitDecoder* d) {
     cudaFree(d->x); cudaFree(d->h); cudaFree(d->big); cudaFree(d->cu_dev);
     cudaFree(d->logits_scratch); cudaFree(d->row_loss); cudaFree(d->row_valid);
     cudaFree(d->kv_cache); cudaFree(d->gen_ids); cudaFree(d->gen_done); cudaFree(d->last_h);
+    if (d->order.tail) cudaEventDestroy(d->order.tail);
     delete d;
 }
 
@@ -290,8 +290,6 @@ int git_decoder_create(const float* params_host, uint64_t n_params, int vocab, i
     d->vocab_pad = (vocab + 255) / 256 * 256;               // the GEMM's N tile
     d->n_layers = n_layers;
     d->max_rows = max_rows;
-    const char* dbg = getenv("SASVQA_DEBUG_SIMT_GEMM");
-    d->use_simt = dbg != nullptr && dbg[0] == '1';
 
     float* raw = nullptr;
     TRYCUDA(cudaMalloc(&raw, n_params * sizeof(float)));
@@ -387,6 +385,7 @@ int git_decoder_create(const float* params_host, uint64_t n_params, int vocab, i
         TRY(make_tensor_map_bf16_kmajor(&Ly.m_fc1, Ly.w_fc1, kFfn, kHidden, 128));
         TRY(make_tensor_map_bf16_kmajor(&Ly.m_fc2, Ly.w_fc2, kHidden, kFfn, 128));
     }
+    TRYCUDA(cudaEventCreateWithFlags(&d->order.tail, cudaEventDisableTiming));
 #undef TRY
 #undef TRYCUDA
     *out = d;
@@ -416,6 +415,7 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
     const long long S = (long long)n_vis + L;
     SASVQA_REQUIRE(S <= d->max_rows, "one sample's sequence does not fit the decoder workspace (raise max_rows)");
     SASVQA_REQUIRE(hidden_or_null == nullptr || (long long)B * S <= d->max_rows, "hidden-state inspection needs one pass");
+    StreamOrder order(&d->order, s);
     const int group = (int)std::min<long long>(B, d->max_rows / S);
     if ((size_t)(group + 1) * sizeof(int32_t) > d->cu_cap) {
         if (d->cu_dev) SASVQA_CUDA_CHECK(cudaFree(d->cu_dev));
@@ -564,6 +564,7 @@ int git_vqa_generate(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frame
     SASVQA_REQUIRE(frames != nullptr && prompt != nullptr && out_ids != nullptr, "null argument");
     const int n_vis = K * kTokens, Lmax = max_length;
     SASVQA_REQUIRE((long long)n_vis <= d->max_rows && (long long)Lmax <= d->max_rows, "one sample does not fit the workspace");
+    StreamOrder order(&d->order, s);
     const int group = (int)std::min<long long>(B, std::min<long long>(d->max_rows / n_vis, d->max_rows / Lmax));
     int rc;
     const size_t kv_rows = (size_t)group * n_vis;

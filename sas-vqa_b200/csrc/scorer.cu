@@ -60,7 +60,6 @@ struct SasvqaScorer {
     int device = 0;
     int num_sms = 148;
     int vocab = 0, labels = 0, max_tokens = 0;
-    bool use_simt = false;
     __nv_bfloat16* arena_bf16 = nullptr;
     float* arena_f32 = nullptr;
     float *word = nullptr, *pos = nullptr, *type_emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
@@ -82,6 +81,7 @@ struct SasvqaScorer {
     int32_t* idx_dev = nullptr;
     size_t idx_cap = 0;
     cudaStream_t stream = nullptr;
+    WorkspaceOrder order;           // serialises the entry points across the streams they are called on
     bool profile = false;
     std::vector<ScorerProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
@@ -124,7 +124,6 @@ struct SScope {
 int sgemm(SasvqaScorer* e, int kind, const GemmArgs& g, const CUtensorMap* ma, const CUtensorMap* mb, const CUtensorMap* mo,
           cudaStream_t s) {
     SScope sc(e, kind, s);
-    if (e->use_simt) return launch_gemm_simt(g, s);
     return launch_gemm_tcgen05(g, ma, mb, mo, e->num_sms, s);
 }
 
@@ -217,6 +216,7 @@ void scorer_destroy(SasvqaScorer* e) {
     for (const ScorerProfRec& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->order.tail) cudaEventDestroy(e->order.tail);
     delete e;
 }
 
@@ -243,8 +243,6 @@ int scorer_create(const float* params_host, uint64_t n_params, int vocab, int la
     e->vocab = vocab;
     e->labels = labels;
     e->max_tokens = max_tokens;
-    const char* dbg = getenv("SASVQA_DEBUG_SIMT_GEMM");
-    e->use_simt = dbg != nullptr && dbg[0] == '1';
 
     float* raw = nullptr;
     TRYCUDA(cudaMalloc(&raw, n_params * sizeof(float)));
@@ -340,6 +338,7 @@ int scorer_create(const float* params_host, uint64_t n_params, int vocab, int la
         TRY(make_tensor_map_bf16_kmajor(&Ly.m_fc2, Ly.w_fc2, kHidden, kFfn, 128));
     }
     TRYCUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreateWithFlags(&e->order.tail, cudaEventDisableTiming));
 #undef TRY
 #undef TRYCUDA
     *out = e;
@@ -358,6 +357,7 @@ int scorer_logits(SasvqaScorer* e, const int32_t* ids, const int32_t* type_ids, 
     SASVQA_REQUIRE(L >= 1 && L <= kBertMaxPos, "padded length must be in [1, 512] (BERT position table)");
     SASVQA_REQUIRE(ids != nullptr && lengths_host != nullptr && (logits != nullptr || hidden_or_null != nullptr), "null argument");
     SASVQA_REQUIRE(n_layers >= 0 && n_layers <= kLayers, "bad layer count");
+    StreamOrder order(&e->order, s);
     std::vector<int32_t> cu;
     if (int rc = upload_offsets(e, lengths_host, N, L, cu, s)) return rc;
     SASVQA_REQUIRE(hidden_or_null == nullptr || cu[N] <= e->max_tokens, "hidden-state inspection needs one group");
@@ -439,13 +439,19 @@ int scorer_logits_host(SasvqaScorer* e, const int64_t* ids, const int64_t* type_
     SASVQA_REQUIRE(L >= 1 && L <= kBertMaxPos, "padded length must be in [1, 512] (BERT position table)");
     std::vector<int32_t> ids32, type32, lens;
     if (int rc = pack_host_inputs(ids, type_ids, mask, N, L, e->vocab, ids32, type32, lens)) return rc;
-    if (int rc = stage_host_inputs(e, ids32, type32, type_ids != nullptr, N)) return rc;
-    if (int rc = scorer_logits(e, e->ids_dev, type_ids ? e->type_dev : nullptr, lens.data(), N, L, e->logits_dev, kLayers,
-                               nullptr, e->stream))
-        return rc;
-    SASVQA_CUDA_CHECK(cudaMemcpyAsync(logits_host, e->logits_dev, (size_t)N * e->labels * sizeof(float), cudaMemcpyDeviceToHost,
-                                      e->stream));
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    auto run = [&]() -> int {
+        if (int rc = stage_host_inputs(e, ids32, type32, type_ids != nullptr, N)) return rc;
+        if (int rc = scorer_logits(e, e->ids_dev, type_ids ? e->type_dev : nullptr, lens.data(), N, L, e->logits_dev, kLayers,
+                                   nullptr, e->stream))
+            return rc;
+        SASVQA_CUDA_CHECK(cudaMemcpyAsync(logits_host, e->logits_dev, (size_t)N * e->labels * sizeof(float),
+                                          cudaMemcpyDeviceToHost, e->stream));
+        return 0;
+    };
+    const int rc = run();
+    const cudaError_t ce = cudaStreamSynchronize(e->stream);    // on failure too: nothing stays in flight on the caller's buffers
+    if (rc) return rc;
+    SASVQA_CUDA_CHECK(ce);
     return 0;
 }
 
@@ -463,22 +469,31 @@ int mif_select_captions_host(SasvqaScorer* e, const int64_t* ids, const int64_t*
     const int N = G * T;
     std::vector<int32_t> ids32, type32, lens;
     if (int rc = pack_host_inputs(ids, type_ids, mask, N, L, e->vocab, ids32, type32, lens)) return rc;
-    if (int rc = stage_host_inputs(e, ids32, type32, type_ids != nullptr, N)) return rc;
-    if (int rc = scorer_logits(e, e->ids_dev, type_ids ? e->type_dev : nullptr, lens.data(), N, L, e->logits_dev, kLayers,
-                               nullptr, e->stream))
-        return rc;
-    if (int rc = sgrow((void**)&e->scores_dev, &e->scores_cap, (size_t)N * sizeof(float))) return rc;
-    if (int rc = sgrow((void**)&e->idx_dev, &e->idx_cap, std::max<size_t>((size_t)G * K, 1) * sizeof(int32_t))) return rc;
-    take_label_kernel<<<(N + 255) / 256, 256, 0, e->stream>>>(e->logits_dev, N, e->labels, label, e->scores_dev);
-    SASVQA_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-    if (K > 0) {
-        if (int rc = launch_topk_strided(e->scores_dev, G, T, ds_rate, K, e->idx_dev, nullptr, e->stream)) return rc;
-        SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host, e->idx_dev, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    }
-    if (scores_host)
-        SASVQA_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->scores_dev, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-    SASVQA_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    auto run = [&]() -> int {
+        if (int rc = stage_host_inputs(e, ids32, type32, type_ids != nullptr, N)) return rc;
+        if (int rc = scorer_logits(e, e->ids_dev, type_ids ? e->type_dev : nullptr, lens.data(), N, L, e->logits_dev, kLayers,
+                                   nullptr, e->stream))
+            return rc;
+        if (int rc = sgrow((void**)&e->scores_dev, &e->scores_cap, (size_t)N * sizeof(float))) return rc;
+        if (int rc = sgrow((void**)&e->idx_dev, &e->idx_cap, std::max<size_t>((size_t)G * K, 1) * sizeof(int32_t))) return rc;
+        StreamOrder order(&e->order, e->stream);
+        take_label_kernel<<<(N + 255) / 256, 256, 0, e->stream>>>(e->logits_dev, N, e->labels, label, e->scores_dev);
+        SASVQA_CUDA_CHECK(cudaGetLastError());
+        count_launch();
+        if (K > 0) {
+            if (int rc = launch_topk_strided(e->scores_dev, G, T, ds_rate, K, e->idx_dev, nullptr, e->stream)) return rc;
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host, e->idx_dev, (size_t)G * K * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                              e->stream));
+        }
+        if (scores_host)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(scores_host, e->scores_dev, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost,
+                                              e->stream));
+        return 0;
+    };
+    const int rc = run();
+    const cudaError_t ce = cudaStreamSynchronize(e->stream);    // on failure too: nothing stays in flight on the caller's buffers
+    if (rc) return rc;
+    SASVQA_CUDA_CHECK(ce);
     return 0;
 }
 

@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(32) mdf_greedy_kernel(const float* __restrict_
         if (p - W > l) push(l, p - W);
         if (p + W < r) push(p + W, r);
     }
+    // fewer than K picks: the tail is defined (-1 = "no frame", gathers as a zero row) -- status 1 rows are overwritten
+    // by the top-K fallback that follows, status 3 rows (T < K, the reference raises) keep their n_picks real picks
+    for (int k = n_picks + lane; k < K; k += 32) out[k] = -1;
     if (lane == 0) status[b] = (n_picks >= K) ? 0 : (T < K ? 3 : 1);
 }
 

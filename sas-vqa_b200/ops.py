@@ -432,25 +432,38 @@ def launch_count() -> int:
 # ---- test hooks
 def test_gemm(a: torch.Tensor, b: torch.Tensor, mode: int, vec: torch.Tensor, out_f32: torch.Tensor = None,
               use_simt: bool = False):
+    """One GEMM with a fused epilogue.  ``use_simt`` runs the CUDA-core check kernel of the TEST-ONLY library
+    (libsasvqa_b200_test.so) instead of the product's tcgen05 kernel."""
     a = _need_cuda(a, torch.bfloat16, "a")
     b = _need_cuda(b, torch.bfloat16, "b")
     M, K = a.shape
     N = b.shape[0]
     out_bf16 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if mode in (0, 1, 4) else None
     with torch.cuda.device(a.device):
-        _capi.check(_capi.lib().sasvqa_test_gemm(a.data_ptr(), b.data_ptr(), M, N, K, mode, vec.data_ptr(),
-                                                 _capi.ptr(out_bf16), _capi.ptr(out_f32), int(use_simt), _stream(a)),
-                    "sasvqa_test_gemm")
+        if use_simt:
+            _capi.check_test(_capi.test_lib().sasvqa_check_gemm_simt(
+                a.data_ptr(), b.data_ptr(), M, N, K, mode, vec.data_ptr(), _capi.ptr(out_bf16), _capi.ptr(out_f32),
+                _stream(a)), "sasvqa_check_gemm_simt")
+        else:
+            _capi.check(_capi.lib().sasvqa_test_gemm(a.data_ptr(), b.data_ptr(), M, N, K, mode, vec.data_ptr(),
+                                                     _capi.ptr(out_bf16), _capi.ptr(out_f32), _stream(a)),
+                        "sasvqa_test_gemm")
     return out_bf16 if mode in (0, 1, 4) else out_f32
 
 
 def test_attention(qkv: torch.Tensor, impl: int = 0) -> torch.Tensor:
+    """The encoder's per-frame attention: impl 0 = the product's tcgen05 kernel, 1 = the mma.sync check kernel of the
+    test-only library, 10 + v = instrumented variant v of the tcgen05 kernel."""
     qkv = _need_cuda(qkv, torch.bfloat16, "qkv")
     n = qkv.shape[0] // TOKENS
     out = torch.empty(n * TOKENS, HIDDEN, dtype=torch.bfloat16, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        _capi.check(_capi.lib().sasvqa_test_attention(qkv.data_ptr(), n, out.data_ptr(), int(impl), _stream(qkv)),
-                    "sasvqa_test_attention")
+        if impl == 1:
+            _capi.check_test(_capi.test_lib().sasvqa_check_attention_mma(qkv.data_ptr(), n, out.data_ptr(), _stream(qkv)),
+                             "sasvqa_check_attention_mma")
+        else:
+            _capi.check(_capi.lib().sasvqa_test_attention(qkv.data_ptr(), n, out.data_ptr(), max(0, int(impl) - 10),
+                                                          _stream(qkv)), "sasvqa_test_attention")
     return out
 
 

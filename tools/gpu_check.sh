@@ -14,6 +14,5 @@ run() { # name timeout cmd...
 : > gpurun_out/summary.log
 run t1_nogemm 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "simt or layernorm or attention or preprocess or gather or scores or select or topk" --maxfail=20
 run t2_tcgen05 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "tcgen05" --maxfail=20
-SASVQA_DEBUG_SIMT_GEMM=1 run t3_pipeline_simt 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "encoder or e2e or edge" --maxfail=20
 run t4_pipeline 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "encoder or e2e or edge or full_size" --maxfail=20
 run t5_smoke 300 python -c "import __graft_entry__ as g; g.smoke()"
