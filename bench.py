@@ -12,13 +12,17 @@ encoder); ranks own disjoint clip ids (weak scaling) and all-gather the index ta
 `e2e`    : the same step through the host-buffer C-ABI call (sasvqa_mdf_sample_host): pinned host
            clips in, indices + sampled frames back in host memory, copies inside the timed region.
 `roofline`: the dominant kernel (tcgen05 encoder GEMM), timed live with CUDA events on its stream.
-`cpu_baseline` / `--impl reference`: the reference's CPU path (HF GitVisionModel fp32 + the oracle
-           restatement of its sampler, proven identical in tests/) on the box's host cores, on a
-           bounded sample (one clip of the same shape per step).
+`cpu_baseline` / `--impl reference`: the reference's OWN sampler (sample_representative_frames, unmodified, from
+           oracle/_ref or /root/reference) driving the HF GitVisionModel it loads (fp32) on the box's host cores, on a
+           bounded sample of the same clips; timed both as the reference runs it (autograd on) and under no_grad.
+`--scaling strong`: --clips is the GLOBAL clip count, sharded over the ranks (weak: --clips per GPU).
+At N > 1 rank 0 re-samples 8 clips of the global list unsharded and compares them with the all-gathered table
+(`sharding_check`, outside the timed region).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -45,7 +49,34 @@ HBM_STAGE_BYTES_PER_FRAME = {
     "pool_norm": 197 * 768 * 4 + 768 * 4,                # fp32 hidden state in, one unit feature row out
     "attention": 12 * 197 * (2304 * 2 + 768 * 2),        # q|k|v read once, heads written once (12 layers)
 }
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = {2048: (2.428e9 + 3.041e9 + 3.047e9 + 5.158e9) / 4}
+NCU_GEMM_SUMMARY = os.path.join(ROOT, "profiles", "r02", "ncu_gemm.json")      # written by tools/summarize_ncu.py
+GEMM_SOURCES = ("gemm_tcgen05.cu", "common.cuh")                                 # what the capture's hash covers
+E2E_PINNED_BYTES_CAP = 9e9                                                        # pinned host memory per rank for the e2e leg
+
+
+def gemm_source_hash() -> str:
+    h = hashlib.sha256()
+    for name in GEMM_SOURCES:
+        with open(os.path.join(ROOT, "sas-vqa_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_gemm_traffic(chunk_frames: int):
+    """(mean DRAM bytes per GEMM launch, note) from the committed ncu summary -- refused (None) when the summary was
+    captured on other GEMM sources or another chunk size than this run's."""
+    try:
+        summ = json.load(open(NCU_GEMM_SUMMARY))
+    except (OSError, ValueError):
+        return None, "no ncu summary at profiles/r02/ncu_gemm.json"
+    if summ.get("source_sha256_16") != gemm_source_hash():
+        return None, (f"profiles/r02/ncu_gemm.json was captured on other GEMM sources (hash {summ.get('source_sha256_16')} != "
+                      f"{gemm_source_hash()}): re-capture with tools/gpu_profile.sh")
+    if int(summ.get("chunk_frames", 0)) != int(chunk_frames):
+        return None, f"ncu summary is for chunk_frames={summ.get('chunk_frames')}, this run uses {chunk_frames}"
+    return float(summ["mean_dram_bytes_per_launch"]), (
+        f"mean dram__bytes_read+write per per-layer GEMM launch from `ncu --set full` ({summ.get('capture', '?')}); per mode: "
+        + ", ".join(f"{k} {v['dram_bytes'] / 1e9:.2f} GB / tensor pipe {v['tensor_pipe_pct']:.0f} %" for k, v in summ["modes"].items()))
 
 
 # Per-GPU shapes of the BASELINE.json configs.  c2 is the metric's configuration (the default, the only one the
@@ -93,10 +124,14 @@ def parse():
     ap.add_argument("--ds-rate", type=int, default=1, help="MIF stride (workload c3)")
     ap.add_argument("--chunk-frames", type=int, default=2048)
     ap.add_argument("--max-tokens", type=int, default=131072, help="packed tokens per scorer pass (workload c3x)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --clips per GPU; strong: --clips is the global clip list, sharded over the ranks")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-clips", type=int, default=None,
+                    help="clips per GPU per e2e step (default: the step's own batch, capped to ~9 GB of pinned memory)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-clips", type=int, default=1, help="clips in the CPU baseline sample")
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the CPU baseline sample")
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     for k in ("clips", "frames", "K", "W"):
@@ -171,11 +206,11 @@ def physical_gpu_index(local_rank: int) -> int:
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_setup():
-    """The reference's CPU path: HF GitVisionModel (fp32, the third-party encoder it loads) driven
-    by the restated sampler (oracle/mdf.py == src/preprocessing/datautils/utils.py:31-94, proven by
-    tests/test_oracle_golden.py).  /root/reference itself does not exist on the GPU box."""
+    """The reference's CPU path: its OWN sample_representative_frames (src/preprocessing/datautils/utils.py:31-94, executed
+    unmodified from oracle/_ref -- or /root/reference where that exists) driving the encoder it loads, HF GitVisionModel
+    (fp32).  Falls back to the restated sampler (oracle/mdf.py, proven identical in tests/) only when neither tree is there."""
     import torch
-    from oracle import mdf, vit
+    from oracle import mdf, ref_loader, vit
     from sasvqa_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.random_encoder_state_dict(synth.REF_SEED)
@@ -185,29 +220,65 @@ def cpu_reference_setup():
     except Exception:  # noqa: BLE001  (transformers missing)
         model = vit.VitOracle(sd)
         enc_name = "oracle ViT restatement fp32"
-    return mdf, vit, synth, model, enc_name
+    if ref_loader.available():
+        fn, _ = ref_loader.load_sampler_fns()
+        kind, fn_name = "reference", f"the reference's own sample_representative_frames ({ref_loader.source_kind()})"
+    else:
+        fn = lambda fr, m, K, W, dc: mdf.sample_representative_frames(fr, m, K, W, dc)   # noqa: E731
+        kind, fn_name = "port", "restated sampler (oracle/mdf.py)"
+    return dict(fn=fn, kind=kind, fn_name=fn_name, model=model, enc_name=enc_name, mdf=mdf, vit=vit, synth=synth)
+
+
+def picked_indices(frames, picked):
+    """Indices of the returned frames inside the clip (the reference returns frames, never indices)."""
+    flat = frames.flatten(1)
+    out = []
+    for f in picked.flatten(1):
+        hit = (flat == f).all(dim=1).nonzero().flatten().tolist()
+        out.append(hit[0] if hit else -1)
+    return out
 
 
 def cpu_reference_time(args, n_clips: int, repeats: int, warm: int, u8_clips=None):
-    """Per-step seconds for the reference CPU sampler on `n_clips` clips/step.  `u8_clips`: the
-    very clips the GPU arm sampled (uint8 [n, T, 224, 224, 3] on the host); else generated here."""
+    """Times the reference CPU sampler on `n_clips` clips per step, `repeats` timed steps after `warm` untimed ones, in
+    BOTH modes of BASELINE.md section 4: exactly as the reference runs it (no torch.no_grad, utils.py:39-48) and under
+    torch.no_grad().  `u8_clips`: the very clips the GPU arm sampled (uint8 [n, T, H, W, 3] on the host); else generated
+    here.  Returns dict(times_grad, times_no_grad, picks (of the last clip), ...)."""
     import torch
-    mdf, vit, synth, model, enc_name = cpu_reference_setup()
+    ctx = cpu_reference_setup()
+    synth, vit = ctx["synth"], ctx["vit"]
     if u8_clips is None:
-        u8_clips = [synth.make_clip(cid, args.frames) for cid in range(n_clips)]
-    clips = [vit.image_processor_224(u8_clips[i]) for i in range(n_clips)]
-    times, picks = [], None
-    with torch.no_grad():
-        for it in range(warm + repeats):
-            t0 = time.perf_counter()
-            for fr in clips:
-                _, aux = mdf.sample_representative_frames(fr, model, args.K, args.W, {"Failure": 0, "Zeros": 0},
-                                                          return_aux=True)
-            dt = time.perf_counter() - t0
-            if it >= warm:
-                times.append(dt)
-            picks = aux["indices"]
-    return times, enc_name, torch.get_num_threads(), picks, aux
+        u8_clips = [synth.make_clip(cid, args.frames, H=args.height, W=args.width) for cid in range(n_clips)]
+    if args.height == 224 and args.width == 224:
+        clips = [vit.image_processor_224(u8_clips[i]) for i in range(n_clips)]
+        proc = "CLIPImageProcessor arithmetic (rescale + normalise; 224x224 input)"
+    else:
+        try:                                                    # what the reference calls (prefetch_loader.py:74-75)
+            from transformers import CLIPImageProcessor
+            hf_proc = CLIPImageProcessor()
+            clips = [hf_proc(images=list(u8_clips[i].numpy()), return_tensors="pt")["pixel_values"] for i in range(n_clips)]
+            proc = "HF CLIPImageProcessor (bicubic shortest-edge resize + centre crop + rescale + normalise), untimed"
+        except Exception:  # noqa: BLE001
+            from oracle import resize
+            clips = [vit.image_processor_224(torch.from_numpy(resize.resize_crop_u8(u8_clips[i].numpy()))) for i in range(n_clips)]
+            proc = "image processor restatement (oracle/resize.py), untimed"
+    out = {"times_grad": [], "times_no_grad": [], "kind": ctx["kind"], "threads": torch.get_num_threads(),
+           "what": f"{ctx['fn_name']} + {ctx['enc_name']}; frames from the {proc}"}
+    for mode in ("grad", "no_grad"):
+        with (torch.no_grad() if mode == "no_grad" else torch.enable_grad()):
+            for it in range(warm + repeats):
+                t0 = time.perf_counter()
+                for fr in clips:
+                    picked = ctx["fn"](fr, ctx["model"], args.K, args.W, {"Failure": 0, "Zeros": 0})
+                dt = time.perf_counter() - t0
+                if it >= warm:
+                    out["times_" + mode].append(dt)
+    out["picks"] = picked_indices(clips[-1], picked)
+    with torch.no_grad():     # the oracle's scores of the same clip (to size a tie when the two arms differ)
+        _, aux = ctx["mdf"].sample_representative_frames(clips[-1], ctx["model"], args.K, args.W, {"Failure": 0, "Zeros": 0},
+                                                         return_aux=True)
+    out["lcl_avg"] = aux["lcl_avg"]
+    return out
 
 
 def run_reference_captions(args):
@@ -255,41 +326,72 @@ def run_reference_captions(args):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores, rank 0 only.
+    One step = `--cpu-clips` clips of the workload's shape (a bounded sample of the batch); `--steps` timed steps after at
+    most one warm-up step, in both modes; `value` = clips / best step of the FASTER mode (the conservative denominator)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if args.kind == "mif-captions":
         return run_reference_captions(args)
-    times, enc_name, threads, _, _ = cpu_reference_time(args, args.cpu_clips, max(1, args.steps),
-                                                        max(0, min(args.warmup, 1)))
-    per_step = sum(times) / len(times)
-    value = args.cpu_clips / per_step
+    warm = max(0, min(args.warmup, 1))
+    r = cpu_reference_time(args, args.cpu_clips, max(1, args.steps), warm)
+    v_grad = args.cpu_clips / min(r["times_grad"])
+    v_nograd = args.cpu_clips / min(r["times_no_grad"])
+    value = max(v_grad, v_nograd)
+    per_step = args.cpu_clips / value
     sample = (f"{args.cpu_clips} clip(s) x {args.frames} frames per step (bounded sample of the {args.clips}-clip batch), "
-              f"{enc_name} + restated sampler, torch.no_grad, {threads} threads")
+              f"{r['what']}, best of {len(r['times_grad'])} steps per mode after {warm} warm-up, {r['threads']} threads")
+    if args.kind in ("mdf+vqa", "mdf+vqa-full", "mif"):
+        sample += "; the CPU arm runs the MDF sampler only (no downstream forward / question scoring), i.e. LESS work than the GPU arm"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": max(0, min(args.warmup, 1)), "ms_per_step": per_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(r["times_grad"]),
+        "warmup": warm, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "frames_per_s": value * args.frames,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": r["kind"], "sample": sample,
+                         "as_reference_runs_it": {"value": v_grad, "note": "no torch.no_grad (utils.py:39-48 builds autograd graphs)",
+                                                  "step_s": [round(t, 3) for t in r["times_grad"]]},
+                         "under_no_grad": {"value": v_nograd, "step_s": [round(t, 3) for t in r["times_no_grad"]]},
+                         "value_is": "the faster of the two modes", "host_cpu_count": os.cpu_count(),
+                         "indices_last_clip": r["picks"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 def workload_config(args, n_gpus):
+    n_total = args.clips if args.scaling == "strong" else args.clips * n_gpus
+    per_gpu = (n_total + n_gpus - 1) // n_gpus
     return {
-        "workload": args.desc.format(clips=args.clips, frames=args.frames, K=args.K, W=args.W) +
+        "workload": args.desc.format(clips=per_gpu, frames=args.frames, K=args.K, W=args.W) +
                     ", random-init ViT-B/16 encoder",
-        "clips_per_gpu": args.clips, "frames_per_clip": args.frames, "K": args.K, "W": args.W,
-        "global_clips": args.clips * n_gpus, "parallelism": f"dp{n_gpus} (clips sharded by rank)",
-        "l2": f"inputs larger than L2 ({args.clips * args.frames * args.height * args.width * 3 / 1e9:.1f} GB uint8 per GPU "
+        "clips_per_gpu": per_gpu, "frames_per_clip": args.frames, "K": args.K, "W": args.W,
+        "global_clips": n_total, "parallelism": f"dp{n_gpus} (clips sharded by rank)",
+        "l2": f"inputs larger than L2 ({per_gpu * args.frames * args.height * args.width * 3 / 1e9:.1f} GB uint8 per GPU "
               f"streamed once per step)",
     }
 
 
 # ------------------------------------------------------------------------------------------------
+class EnergyMeter:
+    """NVML total-energy counter of one GPU (mJ since driver load): joules over a region = the difference."""
+
+    def __init__(self, index: int):
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.read()
+        except Exception:  # noqa: BLE001
+            self.h = None
+
+    def read(self):
+        return self.nv.nvmlDeviceGetTotalEnergyConsumption(self.h) / 1e3 if self.h is not None else None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -307,10 +409,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
-    B, T, K, W = args.clips, args.frames, args.K, args.W
+    T, K, W = args.frames, args.K, args.W
+    vqa = args.kind in ("mdf+vqa", "mdf+vqa-full")
     enc = sas.FrameEncoder(synth.random_encoder_state_dict(synth.REF_SEED), chunk_frames=args.chunk_frames)
-    n_total = B * world
+    n_total = args.clips if args.scaling == "strong" else args.clips * world
     start, end = sharding.shard_range(n_total, rank, world)
+    B = end - start                                                  # this rank's clips (strong: differs by <= 1 over ranks)
     clips = synth.make_clips(range(start, end), T, device=dev, H=args.height, W=args.width)   # uint8, resident in HBM
     q = synth.question_embeddings(range(start, end), device=dev) if args.kind == "mif" else None
     ragged_lengths = None
@@ -323,15 +427,34 @@ def run_ours(args):
             lens[int(lens.argmax())] -= K
         ragged_lengths = lens.tolist()
         ragged_frames = clips.view(B * T, args.height, args.width, 3)
-    dec, qids = None, None
+    dec, qids_all = None, None
+    vqa_ev = []
     if args.kind == "mdf+vqa-full":
         dec = sas.GitDecoder(synth.random_git_decoder_state_dict(), max_rows=131072)
-        qids = torch.randint(1000, synth.GIT_VOCAB, (B, 20), generator=torch.Generator().manual_seed(5)).to(dev)
-        vqa_ev = []
-    if args.kind in ("mdf+vqa", "mdf+vqa-full"):
+        qids_all = torch.randint(1000, synth.GIT_VOCAB, (n_total, 20), generator=torch.Generator().manual_seed(5))
+        qids = qids_all[start:end].to(dev)
+    if vqa:
         psd = synth.random_projection_state_dict()
         enc.set_projection(*[psd[f"visual_projection.{k}"] for k in ("0.weight", "0.bias", "1.weight", "1.bias")])
     torch.cuda.synchronize()
+
+    def downstream(frames_dev, q_ids, res, record):
+        """configs[4]: the video-QA forward on the sampled frames (visual side only for c5, the whole forward for c5x)"""
+        n = frames_dev.shape[0]
+        if args.kind == "mdf+vqa":
+            for b0 in range(0, n, 256):
+                res["tokens_probe"] = sas.encode_sampled_frames(frames_dev[b0:b0 + 256], enc)[:, ::197, :8]
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            answers = []
+            for b0 in range(0, n, 64):
+                logits = sas.vqa_logits(frames_dev[b0:b0 + 64], q_ids[b0:b0 + 64], enc, dec)
+                answers.append(logits[:, -1, :].argmax(dim=-1))
+            res["answer_probe"] = torch.cat(answers)
+            e1.record()
+            if record:
+                vqa_ev.append((e0, e1))
 
     def step():
         if args.kind == "mdf-ragged":
@@ -341,17 +464,8 @@ def run_ours(args):
             res["status"] = torch.zeros(B, dtype=torch.int32, device=dev)
         else:
             res = sas.sample_mdf_batch(clips, enc, K, W, want_frames=True)
-        if args.kind == "mdf+vqa":                               # the downstream forward's visual side, 256 clips at a time
-            for b0 in range(0, B, 256):
-                res["tokens_probe"] = sas.encode_sampled_frames(res["frames"][b0:b0 + 256], enc)[:, ::197, :8]
-        if args.kind == "mdf+vqa-full":                          # the whole downstream forward: next-token logits of the question
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for b0 in range(0, B, 64):
-                logits = sas.vqa_logits(res["frames"][b0:b0 + 64], qids[b0:b0 + 64], enc, dec)
-                res["answer_probe"] = logits[:, -1, :].argmax(dim=-1)
-            e1.record()
-            vqa_ev.append((e0, e1))
+        if vqa:
+            downstream(res["frames"], qids if dec is not None else None, res, True)
         table = sharding.all_gather_rows(res["indices"], n_total) if world > 1 else res["indices"]
         return res, table
 
@@ -365,15 +479,19 @@ def run_ours(args):
     barrier()
     launches0 = ops.launch_count()
     enc.profile_enable(True)
-    sampler_thread = ClockSampler(physical_gpu_index(local_rank))
+    gpu_index = physical_gpu_index(local_rank)
+    sampler_thread = ClockSampler(gpu_index)
+    energy = EnergyMeter(gpu_index)
     sampler_thread.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    j0 = energy.read()
     ev0.record()
     for _ in range(args.steps):
         res, table = step()
     ev1.record()
     barrier()
+    j1 = energy.read()
     clocks = sampler_thread.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     prof = enc.profile_read()
@@ -386,20 +504,20 @@ def run_ours(args):
     ms_per_step = elapsed_ms / args.steps
     value = n_total / (ms_per_step / 1e3)
     status = res["status"].cpu()
+    idx_cpu = res["indices"].cpu()
 
     # ---- roofline of the dominant kernel (all five GEMM shapes run the same tcgen05 kernel)
     gemm_ms = sum(prof[k][0] for k in prof if k.startswith("gemm_"))
     gemm_launches = sum(prof[k][1] for k in prof if k.startswith("gemm_"))
-    frames_per_step = B * T + (B * K if args.kind in ("mdf+vqa", "mdf+vqa-full") else 0)   # c5 encodes the K picks a second time
+    frames_per_step = B * T + (B * K if vqa else 0)                  # c5 encodes the K picks a second time
     frames_timed = frames_per_step * args.steps
     achieved_tf = GEMM_FLOP_PER_FRAME * frames_timed / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     stage_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items()}
+    traffic, traffic_note = ncu_gemm_traffic(enc.chunk_frames)
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved_tf, "peak": peaks["tf_sustained"],
         "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sustained"],
-        "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH.get(args.chunk_frames),
-        "traffic_note": "mean DRAM bytes per GEMM launch from ncu (profiles/r01/ncu_gemm_v6_full.txt); algorithmic "
-                        "operand+result bytes average 3.4e9 per launch at this chunk size",
+        "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
         "flop_per_launch": GEMM_FLOP_PER_FRAME * frames_timed / max(gemm_launches, 1),
         "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches": gemm_launches,
@@ -408,6 +526,11 @@ def run_ours(args):
         "whole_path_frac_of_sustained": TOTAL_FLOP_PER_FRAME * frames_per_step / (ms_per_step / 1e3) / 1e12 / peaks["tf_sustained"],
         "stage_ms_per_step": stage_ms,
     }
+    if j0 is not None and j1 is not None:
+        joules = (j1 - j0) / args.steps
+        roofline["energy"] = {"joules_per_step": round(joules, 1), "avg_power_w": round(joules / (ms_per_step / 1e3), 1),
+                              "pj_per_flop_whole_path": round(joules / (TOTAL_FLOP_PER_FRAME * frames_per_step) * 1e12, 4),
+                              "source": "nvmlDeviceGetTotalEnergyConsumption around the timed region (this rank's GPU)"}
 
     # achieved GB/s of the HBM-bound stages, from the same CUDA-event scopes
     hbm = {}
@@ -430,19 +553,91 @@ def run_ours(args):
     roofline["hbm_stages"] = hbm
     roofline["hbm_peak_gbs"] = peaks["hbm"]
 
-    # ---- end to end through the host-buffer C-ABI call
+    # ---- fallback clips whose picks include exact-0.0 border scores (lcl_avg[i < W or i >= T - W] == 0, utils.py:57-61): there
+    # the order among equal scores is torch.topk's on the CPU and lowest-index-first here, so the stored frames may differ
+    st_counts = {"greedy": int((status == 0).sum()), "fallback": int((status == 1).sum()), "empty": int((status == 2).sum()),
+                 "too_few": int((status == 3).sum())}
+    if args.kind in ("mdf", "mdf+vqa", "mdf+vqa-full"):
+        Wr = T // 20 if W == -1 else W
+        border = (idx_cpu < Wr) | (idx_cpu >= T - Wr)
+        st_counts["fallback_zero_border_clips"] = int(((status == 1) & border.any(dim=1)).sum())
+
+    # ---- sharding invariance (N > 1): rank 0 re-samples 8 clips of the GLOBAL list on its own and compares with the gathered table
+    sharding_check = None
+    if world > 1 and rank == 0:
+        if args.kind == "mdf-ragged":
+            sharding_check = {"skipped": "ragged clips are cut from each rank's own frame stream; see tests/test_gpu_multi.py"}
+        else:
+            ids = sorted({int(round(i * (n_total - 1) / 7)) for i in range(8)})
+            probe = synth.make_clips(ids, T, device=dev, H=args.height, W=args.width)
+            if args.kind == "mif":
+                alone = sas.sample_mif_batch(probe, enc, synth.question_embeddings(ids, device=dev), K, args.ds_rate)["indices"]
+            else:
+                alone = sas.sample_mdf_batch(probe, enc, K, W, want_frames=False)["indices"]
+            same = torch.equal(alone.cpu(), table.cpu()[torch.tensor(ids)])
+            sharding_check = {"clips": len(ids), "clip_ids": ids, "identical": bool(same),
+                              "how": "rank 0 regenerates these global clips, samples them unsharded (one 8-clip call) and compares "
+                                     "the indices with the rows of the all-gathered table (outside the timed region)"}
+            del probe
+
+    # ---- end to end through the host-buffer C-ABI calls: pinned host inputs, results back in host memory, every copy timed
     e2e = None
-    if not args.no_e2e and args.kind == "mdf":
-        host_clips = torch.empty(clips.shape, dtype=torch.uint8, pin_memory=True)
-        host_clips.copy_(clips)
-        idx_h = torch.empty(B, K, dtype=torch.int32, pin_memory=True)
-        st_h = torch.empty(B, dtype=torch.int32, pin_memory=True)
-        fr_h = torch.empty(B, K, 3, 224, 224, dtype=torch.float32, pin_memory=True)
+    if not args.no_e2e:
+        bytes_per_clip = T * args.height * args.width * 3 + K * ops.FRAME_ELEMS * 4
+        nb = args.e2e_clips or max(1, min(B, int(E2E_PINNED_BYTES_CAP // bytes_per_clip)))
+        nb = min(nb, B)
+        if world > 1 and args.scaling == "strong":                   # every rank the same e2e batch so the global count is exact
+            t_nb = torch.tensor([nb], device=dev)
+            dist.all_reduce(t_nb, op=dist.ReduceOp.MIN)
+            nb = int(t_nb.item())
+        host_clips = torch.empty((nb,) + tuple(clips.shape[1:]), dtype=torch.uint8, pin_memory=True)
+        host_clips.copy_(clips[:nb])
+        idx_h = torch.empty(nb, K, dtype=torch.int32, pin_memory=True)
+        st_h = torch.empty(nb, dtype=torch.int32, pin_memory=True)
+        fr_h = torch.empty(nb, K, 3, 224, 224, dtype=torch.float32, pin_memory=True)
+        h2d, d2h = int(host_clips.numel()), int(idx_h.numel() * 4 + st_h.numel() * 4 + fr_h.numel() * 4)
+        if args.kind == "mdf-ragged":
+            cum, nclip = 0, 0
+            while nclip < B and cum + ragged_lengths[nclip] <= nb * T:
+                cum += ragged_lengths[nclip]
+                nclip += 1
+            host_frames = host_clips.view(nb * T, args.height, args.width, 3)[:cum]
+            api = "sasvqa_mdf_sample_ragged_host"
+            n_e2e, h2d = nclip, int(host_frames.numel())
+            d2h = n_e2e * (K * 4 + 4 + K * ops.FRAME_ELEMS * 4)
+        elif args.kind == "mif":
+            q_h = q[:nb].cpu().pin_memory()
+            api, n_e2e = "sasvqa_mif_sample_host_hw", nb
+            h2d += int(q_h.numel() * 4)
+            d2h -= int(st_h.numel() * 4)
+        else:
+            api, n_e2e = "sasvqa_mdf_sample_host_hw", nb
+        if vqa:
+            ans_h = torch.empty(nb, dtype=torch.int64, pin_memory=True)
+            qids_h = qids_all[start:start + nb].to(torch.int32).pin_memory() if dec is not None else None
+            api += " -> sampled frames back to the GPU in batches -> " + ("sasvqa_git_vqa_logits_f32" if dec is not None else
+                                                                            "sasvqa_visual_tokens_f32")
+            h2d += int(fr_h.numel() * 4) + (int(qids_h.numel() * 4) if qids_h is not None else 0)
+            d2h += int(ans_h.numel() * 8) if dec is not None else 0
 
         def e2e_step():
-            out = sas.sample_mdf_host(host_clips, enc, K, W, idx_out=idx_h, status_out=st_h, frames_out=fr_h)
+            if args.kind == "mdf-ragged":
+                out = ops.mdf_sample_ragged_host(enc, host_frames, ragged_lengths[:n_e2e], K, W)
+            elif args.kind == "mif":
+                out = sas.sample_mif_host(host_clips, enc, q_h, K, args.ds_rate, idx_out=idx_h, frames_out=fr_h, want_frames=True)
+            else:
+                out = sas.sample_mdf_host(host_clips, enc, K, W, idx_out=idx_h, status_out=st_h, frames_out=fr_h)
+            if vqa:        # the consumer reads the stored frames back (the reference couples the two programs through the H5 file)
+                r2 = {}
+                for b0 in range(0, nb, 64):
+                    fr_d = fr_h[b0:b0 + 64].to(dev, non_blocking=True)
+                    qd = qids_h[b0:b0 + 64].to(dev, non_blocking=True) if qids_h is not None else None
+                    downstream(fr_d, qd, r2, False)
+                    if dec is not None:
+                        ans_h[b0:b0 + 64].copy_(r2["answer_probe"], non_blocking=True)
+                torch.cuda.synchronize()
             if world > 1:
-                sharding.all_gather_rows(out["indices"].to(dev), n_total)
+                sharding.all_gather_rows(out["indices"].to(dev), n_e2e * world)
             return out
 
         e2e_step()
@@ -455,38 +650,44 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_s = float(dt.item()) / args.e2e_steps
-        assert torch.equal(out["indices"], res["indices"].cpu()), "host path and device path disagree"
-        e2e = {"value": n_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(host_clips.numel()),
-               "d2h_bytes_per_step": int(idx_h.numel() * 4 + st_h.numel() * 4 + fr_h.numel() * 4),
-               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps,
-               "api": "sasvqa_mdf_sample_host (pinned uint8 clips in; indices, status and sampled fp32 frames out)"}
+        assert torch.equal(out["indices"][:n_e2e], idx_cpu[:n_e2e]), "host path and device path disagree"
+        e2e = {"value": n_e2e * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps, "clips_per_gpu_per_step": n_e2e,
+               "api": api + " (pinned host buffers in; indices, status and sampled fp32 frames out)",
+               "indices_equal_device_path": True}
         del host_clips, fr_h
 
-    # ---- CPU baseline (rank 0, N=1 only): the reference CPU sampler on a bounded sample
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own sampler on a bounded sample of this very batch
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.kind == "mdf" and args.height == 224:
-        nc = args.cpu_clips
-        times, enc_name, threads, picks, aux = cpu_reference_time(args, nc, 1, 0, u8_clips=clips[:nc].cpu())
-        cpu_v = nc / min(times)
-        gpu_picks = res["indices"][nc - 1].cpu().tolist()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.kind in ("mdf", "mdf+vqa", "mdf+vqa-full"):
+        nc = max(1, min(args.cpu_clips, B))
+        r = cpu_reference_time(args, nc, 1, 0, u8_clips=clips[:nc].cpu())
+        v_grad, v_nograd = nc / min(r["times_grad"]), nc / min(r["times_no_grad"])
+        picks = r["picks"]
+        gpu_picks = idx_cpu[nc - 1].tolist()
         # same clip, both arms: identical indices unless the deciding scores tie within the bf16-induced error
-        lcl_ref = aux["lcl_avg"]
-        gap = max([abs(float(lcl_ref[a]) - float(lcl_ref[b])) for a, b in zip(gpu_picks, picks) if a != b] or [0.0])
-        cpu = {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
+        lcl_ref = r["lcl_avg"]
+        gap = max([abs(float(lcl_ref[a]) - float(lcl_ref[b])) for a, b in zip(gpu_picks, picks) if a != b and a >= 0 and b >= 0]
+                  or [0.0])
+        cpu = {"value": max(v_grad, v_nograd), "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
                "sample": f"{nc} clip(s) x {T} frames: the first clip(s) of the GPU arm's own batch copied to the host, "
-                         f"{enc_name} + restated sampler, torch.no_grad, 1 timed pass",
+                         f"{r['what']}, 1 timed pass per mode",
+               "as_reference_runs_it": {"value": v_grad, "note": "no torch.no_grad (utils.py:39-48 builds autograd graphs)"},
+               "under_no_grad": {"value": v_nograd}, "value_is": "the faster of the two modes",
+               "host_cpu_count": os.cpu_count(),
                "cpu_indices": picks, "gpu_indices": gpu_picks, "indices_identical": picks == gpu_picks,
                "max_score_gap_where_different": gap}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
             "frames_per_s": value * T, "clocks": clocks, "gpu_launches": int(launches),
-            "status_counts": {"greedy": int((status == 0).sum()), "fallback": int((status == 1).sum())},
-            "roofline": roofline,
+            "status_counts": st_counts, "roofline": roofline,
         }
+        if sharding_check is not None:
+            line["sharding_check"] = sharding_check
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

@@ -104,6 +104,12 @@ int sasvqa_mif_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips_hwc_dev, in
                             const float* q_dev, int K, int ds_rate, int32_t* idx_dev, float* scores_or_null_dev,
                             float* feats_or_null_dev, float* sampled_or_null_dev, void* stream);
 
+/* the same from HOST buffers (clips_hwc_host [B, T, H, W, 3] uint8, q_host [B, 768] fp32; pinned memory makes the copies
+ * asynchronous), streamed through the double-buffered pipeline of sasvqa_mdf_sample_host: idx_host [B, K] and, if not
+ * NULL, the sampled fp32 frames [B, K, 3*224*224] land in host memory before the call returns. */
+int sasvqa_mif_sample_host_hw(SasvqaEncoder* enc, const uint8_t* clips_hwc_host, int B, int T, int H, int W,
+                              const float* q_host, int K, int ds_rate, int32_t* idx_host, float* sampled_or_null_host);
+
 /* ---- K5: gather the selected frames as normalised fp32 rows (utils.py:94, extract_features.py:96)
  * out [B, K, 3*224*224]; out-of-range indices give zero rows. */
 int sasvqa_gather_frames_u8(const uint8_t* clips_hwc_dev, const int32_t* idx_dev, int B, int T, int K,

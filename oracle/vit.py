@@ -34,8 +34,8 @@ def image_processor_224(u8_hwc: torch.Tensor) -> torch.Tensor:
     resize and centre crop are identities): rescale by 1/255 then (x - mean) / std, fp32,
     HWC -> CHW.  Returns (T, 3, 224, 224)."""
     x = u8_hwc.permute(0, 3, 1, 2).to(torch.float32) * (1.0 / 255.0)
-    mean = torch.tensor(IMAGE_MEAN, dtype=torch.float32).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGE_STD, dtype=torch.float32).view(1, 3, 1, 1)
+    mean = torch.tensor(IMAGE_MEAN, dtype=torch.float32, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGE_STD, dtype=torch.float32, device=x.device).view(1, 3, 1, 1)
     return (x - mean) / std
 
 
@@ -46,8 +46,10 @@ def quick_gelu(x: torch.Tensor) -> torch.Tensor:
 class VitOracle:
     """Callable like the reference's ``model``: ``model(frames).last_hidden_state``."""
 
-    def __init__(self, state_dict: dict, dtype=torch.float32):
-        self.w = {k: v.detach().to(dtype) for k, v in state_dict.items()}
+    def __init__(self, state_dict: dict, dtype=torch.float32, device="cpu"):
+        """``device``: where this plain-torch fp32 restatement runs.  The CPU is the pinned oracle (tests/golden); tests
+        that need many clips run the SAME code on the GPU in strict fp32 (TF32 off) after checking it against the CPU."""
+        self.w = {k: v.detach().to(device=device, dtype=dtype) for k, v in state_dict.items()}
         self.dtype = dtype
 
     def _ln(self, x, name):

@@ -20,10 +20,11 @@ from .sampler import (  # noqa: F401
     sample_mdf_host,
     sample_mdf_ragged,
     sample_mif_batch,
+    sample_mif_host,
     sample_representative_frames,
 )
 
 __all__ = [
     "CaptionScorer", "FrameEncoder", "GitDecoder", "vqa_generate", "vqa_logits", "vqa_loss", "SasvqaError", "generate_inds", "encode_sampled_frames", "generate_h5", "mif_select", "sample_frame_indices", "sample_frames_uniform",
-    "sample_mdf_batch", "sample_mdf_host", "sample_mdf_ragged", "sample_mif_batch", "sample_representative_frames", "synth",
+    "sample_mdf_batch", "sample_mdf_host", "sample_mdf_ragged", "sample_mif_batch", "sample_mif_host", "sample_representative_frames", "synth",
 ]

@@ -33,6 +33,7 @@ SIGNATURES = {
     "sasvqa_visual_tokens_u8": (c_int, [_p, _p, c_int, c_int, _p, _p]),
     "sasvqa_mif_scores": (c_int, [_p, _p, c_int, c_int, _p, _p]),
     "sasvqa_mif_sample_u8_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, c_int, c_int, _p, _p, _p, _p, _p]),
+    "sasvqa_mif_sample_host_hw": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, c_int, c_int, _p, _p]),
     "sasvqa_gather_frames_u8": (c_int, [_p, _p, c_int, c_int, c_int, _p, _p]),
     "sasvqa_gather_frames_f32": (c_int, [_p, _p, c_int, c_int, c_int, c_int64, _p, _p]),
     "sasvqa_mdf_sample_u8": (c_int, [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p, _p]),

@@ -23,6 +23,7 @@ int encoder_fwd_hidden(SasvqaEncoder*, const __nv_bfloat16*, int, int, float*, c
 int mdf_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, int, int, int32_t*, int32_t*,
                       float*, float*, float*, cudaStream_t);
 int mdf_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, int, int, int32_t*, int32_t*, float*);
+int mif_sample_host(SasvqaEncoder*, const uint8_t*, int, int, int, int, const float*, int, int, int32_t*, float*);
 int mdf_sample_ragged_host(SasvqaEncoder*, const uint8_t*, int, const int32_t*, int, int, int, int, int32_t*, int32_t*, float*);
 int mdf_sample_ragged_device(SasvqaEncoder*, const uint8_t*, const float*, int, const int32_t*, int, int, int, int, int32_t*,
                              int32_t*, float*, float*, float*, cudaStream_t);
@@ -170,6 +171,13 @@ int sasvqa_mif_sample_u8_hw(SasvqaEncoder* enc, const uint8_t* clips, int B, int
     return guarded([&]() -> int {
         SASVQA_REQUIRE(B == 0 || clips != nullptr, "null clips");
         return mif_sample_device(enc, clips, nullptr, B, T, H, Wd, q, K, ds_rate, idx, scores, feats, sampled, S(stream));
+    });
+}
+
+int sasvqa_mif_sample_host_hw(SasvqaEncoder* enc, const uint8_t* clips_host, int B, int T, int H, int Wd, const float* q_host,
+                              int K, int ds_rate, int32_t* idx_host, float* sampled_host) {
+    return guarded([&]() -> int {
+        return mif_sample_host(enc, clips_host, B, T, H, Wd, q_host, K, ds_rate, idx_host, sampled_host);
     });
 }
 

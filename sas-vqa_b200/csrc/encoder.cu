@@ -108,6 +108,8 @@ struct SasvqaEncoder {
     size_t out_stage_cap[2] = {0, 0};
     int32_t* idx_stage[2] = {nullptr, nullptr};
     size_t idx_stage_cap[2] = {0, 0};
+    float* q_stage[2] = {nullptr, nullptr};
+    size_t q_stage_cap[2] = {0, 0};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     WorkspaceOrder order;             // serialises the entry points across the streams they are called on
     // optional per-stage timing
@@ -220,7 +222,17 @@ int grow(void** p, size_t* cap, size_t need) {
 int encoder_create(const float* params_host, uint64_t n_params, int chunk_frames, SasvqaEncoder** out) {
     SASVQA_REQUIRE(out != nullptr && params_host != nullptr, "null argument");
     SASVQA_REQUIRE(n_params == SASVQA_NUM_ENCODER_PARAMS, "state dict must hold 85 799 424 fp32 values (ViT-B/16)");
-    if (chunk_frames <= 0) chunk_frames = kDefaultChunkFrames;
+    if (chunk_frames <= 0) {
+        // auto-size: the measured-best chunk, or as many frames as half of the free HBM holds (2.1 MB of workspace per frame:
+        // fp32 stream + bf16 operand + the 3072-wide bf16 buffer), in steps of 64 frames
+        chunk_frames = kDefaultChunkFrames;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t per_frame = (size_t)kTokens * (kHidden * sizeof(float) + kHidden * 2 + kFfn * 2);
+            const size_t fit = free_b / 2 / per_frame;
+            if (fit < (size_t)chunk_frames) chunk_frames = (int)std::max<size_t>(64, fit / 64 * 64);
+        }
+    }
     SasvqaEncoder* e = new SasvqaEncoder();
     auto fail = [&](int rc) { sasvqa_encoder_destroy(e); return rc; };
 #define TRY(expr) do { int _rc = (expr); if (_rc) return fail(_rc); } while (0)
@@ -386,7 +398,7 @@ void encoder_destroy(SasvqaEncoder* e) {
     cudaFree(e->feats); cudaFree(e->lcl);
     cudaFree(e->resized); cudaFree(e->picked); cudaFree(e->pick_map); cudaFree(e->clip_off);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(e->stage[i]); cudaFree(e->out_stage[i]); cudaFree(e->idx_stage[i]);
+        cudaFree(e->stage[i]); cudaFree(e->out_stage[i]); cudaFree(e->idx_stage[i]); cudaFree(e->q_stage[i]);
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_comp[i]) cudaEventDestroy(e->ev_comp[i]);
         if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
@@ -716,15 +728,19 @@ static int drain_pipeline(SasvqaEncoder* e) {
 
 // Host-buffer pipeline: groups of whole clips; H2D (h2d_stream), compute (compute_stream) and
 // D2H (d2h_stream) of consecutive groups overlap through two staging slots.
-int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H, int Wd, int K, int W, int32_t* idx_host,
-                    int32_t* status_host, float* sampled_host) {
-    SASVQA_REQUIRE(e != nullptr && idx_host != nullptr && status_host != nullptr, "null argument");
+// q_host != nullptr switches the groups to the MIF path (question embeddings [B, 768] fp32 travel with their clips,
+// ds_rate is the stride of the top-K; W is unused and every status is 0).
+int sample_host_pipeline(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H, int Wd, int K, int W,
+                         const float* q_host, int ds_rate, int32_t* idx_host, int32_t* status_host, float* sampled_host) {
+    const bool mif = q_host != nullptr;
+    SASVQA_REQUIRE(e != nullptr && idx_host != nullptr && (mif || status_host != nullptr), "null argument");
     SASVQA_REQUIRE(B >= 0 && T >= 0 && K >= 1 && W >= -1, "bad B/T/K/W");
     SASVQA_REQUIRE(H > 0 && Wd > 0, "bad frame size");
+    SASVQA_REQUIRE(!mif || (ds_rate >= 1 && T >= 1 && K <= (T + ds_rate - 1) / ds_rate), "selected index k out of range");
     const size_t frame_bytes = (size_t)H * Wd * 3;
     if (B == 0) return 0;
     if (T == 0) {
-        for (int b = 0; b < B; ++b) status_host[b] = SASVQA_STATUS_EMPTY;
+        for (int b = 0; b < B && status_host; ++b) status_host[b] = SASVQA_STATUS_EMPTY;
         for (long long i = 0; i < (long long)B * K; ++i) idx_host[i] = -1;
         if (sampled_host) memset(sampled_host, 0, (size_t)B * K * kFrameElems * sizeof(float));
         return 0;
@@ -738,6 +754,7 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
         if (out_need && (rc = grow((void**)&e->out_stage[i], &e->out_stage_cap[i], out_need))) return rc;
         if ((rc = grow((void**)&e->idx_stage[i], &e->idx_stage_cap[i], (size_t)group * (K + 1) * sizeof(int32_t))))
             return rc;
+        if (mif && (rc = grow((void**)&e->q_stage[i], &e->q_stage_cap[i], (size_t)group * kHidden * sizeof(float)))) return rc;
     }
     const int n_groups = (B + group - 1) / group;
     auto run_group = [&](int gi) -> int {
@@ -747,6 +764,9 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
         if (gi >= 2) SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->h2d_stream, e->ev_comp[slot], 0));
         SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->stage[slot], clips + (size_t)b0 * T * frame_bytes,
                                           (size_t)nb * T * frame_bytes, cudaMemcpyHostToDevice, e->h2d_stream));
+        if (mif)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(e->q_stage[slot], q_host + (size_t)b0 * kHidden, (size_t)nb * kHidden * sizeof(float),
+                                              cudaMemcpyHostToDevice, e->h2d_stream));
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_in[slot], e->h2d_stream));
         SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->compute_stream, e->ev_in[slot], 0));
         // idx/out staging of this slot is free once group gi-2's results are on the host
@@ -754,15 +774,18 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
         int32_t* d_idx = e->idx_stage[slot];
         int32_t* d_status = d_idx + (size_t)group * K;
         float* d_out = sampled_host ? e->out_stage[slot] : nullptr;
-        if (int rc2 = mdf_sample_device(e, e->stage[slot], nullptr, nb, T, H, Wd, K, W, d_idx, d_status, nullptr, nullptr, d_out,
-                                        e->compute_stream))
-            return rc2;
+        const int rc2 = mif ? mif_sample_device(e, e->stage[slot], nullptr, nb, T, H, Wd, e->q_stage[slot], K, ds_rate, d_idx,
+                                                nullptr, nullptr, d_out, e->compute_stream)
+                            : mdf_sample_device(e, e->stage[slot], nullptr, nb, T, H, Wd, K, W, d_idx, d_status, nullptr, nullptr,
+                                                d_out, e->compute_stream);
+        if (rc2) return rc2;
         SASVQA_CUDA_CHECK(cudaEventRecord(e->ev_comp[slot], e->compute_stream));
         SASVQA_CUDA_CHECK(cudaStreamWaitEvent(e->d2h_stream, e->ev_comp[slot], 0));
         SASVQA_CUDA_CHECK(cudaMemcpyAsync(idx_host + (size_t)b0 * K, d_idx, (size_t)nb * K * sizeof(int32_t),
                                           cudaMemcpyDeviceToHost, e->d2h_stream));
-        SASVQA_CUDA_CHECK(cudaMemcpyAsync(status_host + b0, d_status, (size_t)nb * sizeof(int32_t),
-                                          cudaMemcpyDeviceToHost, e->d2h_stream));
+        if (!mif)
+            SASVQA_CUDA_CHECK(cudaMemcpyAsync(status_host + b0, d_status, (size_t)nb * sizeof(int32_t),
+                                              cudaMemcpyDeviceToHost, e->d2h_stream));
         if (sampled_host)
             SASVQA_CUDA_CHECK(cudaMemcpyAsync(sampled_host + (size_t)b0 * K * kFrameElems, d_out,
                                               (size_t)nb * K * kFrameElems * sizeof(float), cudaMemcpyDeviceToHost,
@@ -774,6 +797,18 @@ int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H,
     for (int gi = 0; gi < n_groups && rc == 0; ++gi) rc = run_group(gi);
     const int rc_drain = drain_pipeline(e);     // also on failure: no copy to / from the caller's buffers stays in flight
     return rc ? rc : rc_drain;
+}
+
+int mdf_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H, int Wd, int K, int W, int32_t* idx_host,
+                    int32_t* status_host, float* sampled_host) {
+    return sample_host_pipeline(e, clips, B, T, H, Wd, K, W, nullptr, 1, idx_host, status_host, sampled_host);
+}
+
+// MIF (embedding-space relevance, BASELINE config 3) from host buffers: clips [B, T, H, W, 3] uint8, q [B, 768] fp32
+int mif_sample_host(SasvqaEncoder* e, const uint8_t* clips, int B, int T, int H, int Wd, const float* q_host, int K, int ds_rate,
+                    int32_t* idx_host, float* sampled_host) {
+    SASVQA_REQUIRE(q_host != nullptr, "null question embeddings");
+    return sample_host_pipeline(e, clips, B, T, H, Wd, K, 0, q_host, ds_rate, idx_host, nullptr, sampled_host);
 }
 
 // Host-buffer pipeline for ragged batches: consecutive whole clips are grouped up to chunk_frames frames (a longer clip

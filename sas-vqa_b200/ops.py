@@ -425,6 +425,31 @@ def mif_sample_device(enc: FrameEncoder, clips: torch.Tensor, q: torch.Tensor, K
     return dict(indices=idx, scores=scores, feats=feats, frames=sampled)
 
 
+def mif_sample_host(enc: FrameEncoder, clips_host: torch.Tensor, q_host: torch.Tensor, K: int, ds_rate: int = 1,
+                    idx_out: torch.Tensor = None, frames_out: torch.Tensor = None, want_frames: bool = False) -> dict:
+    """MIF from host memory: clips_host [B, T, H, W, 3] uint8 and q_host [B, 768] fp32 (pinned for full speed); the
+    index table (and the sampled frames) land in host tensors."""
+    if clips_host.is_cuda or clips_host.dtype != torch.uint8 or clips_host.dim() != 5 or clips_host.shape[-1] != 3:
+        raise TypeError("clips_host must be a uint8 CPU tensor [B, T, H, W, 3]")
+    if q_host.is_cuda or q_host.dtype != torch.float32:
+        raise TypeError("q_host must be a float32 CPU tensor")
+    clips_host, q_host = clips_host.contiguous(), q_host.contiguous()
+    B, T, H, Wd = (int(v) for v in clips_host.shape[:4])
+    if tuple(q_host.shape) != (B, HIDDEN):
+        raise ValueError(f"q_host must be [B, 768], got {tuple(q_host.shape)}")
+    pin = torch.cuda.is_available()
+    if idx_out is None:
+        idx_out = torch.empty(B, K, dtype=torch.int32, pin_memory=pin)
+    if frames_out is None and want_frames:
+        frames_out = torch.empty(B, K, 3, IMG, IMG, dtype=torch.float32, pin_memory=pin)
+    with torch.cuda.device(enc.device):
+        _capi.check(_capi.lib().sasvqa_mif_sample_host_hw(enc.handle, clips_host.data_ptr(), B, T, H, Wd, q_host.data_ptr(),
+                                                          int(K), int(ds_rate), idx_out.data_ptr(),
+                                                          _capi.ptr(frames_out) if want_frames else None),
+                    "sasvqa_mif_sample_host_hw")
+    return dict(indices=idx_out, frames=frames_out if want_frames else None)
+
+
 def launch_count() -> int:
     return int(_capi.lib().sasvqa_launch_count())
 

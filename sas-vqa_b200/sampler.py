@@ -173,6 +173,13 @@ def sample_mif_batch(clips: torch.Tensor, model, question_embeds: torch.Tensor, 
                                  want_frames=want_frames, want_aux=want_aux)
 
 
+def sample_mif_host(clips_host: torch.Tensor, model, question_embeds: torch.Tensor, K: int = 8, ds_rate: int = 1, **kw) -> dict:
+    """``sample_mif_batch`` for clips and question embeddings in host memory (pinned for full speed): copies overlap
+    compute in the library's double-buffered pipeline, the index table (and frames) come back in host tensors."""
+    enc = as_frame_encoder(model)
+    return ops.mif_sample_host(enc, clips_host, question_embeds, K, ds_rate, **kw)
+
+
 def encode_sampled_frames(sampled: torch.Tensor, model, project: bool = True) -> torch.Tensor:
     """The visual side of the downstream video-QA forward (src/modeling/modeling.py:76-95,
     ``MyGitModel.forward`` with 5-D ``pixel_values``): ``sampled`` [B, K, 3, 224, 224] fp32 (what the collator

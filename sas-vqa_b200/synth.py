@@ -136,6 +136,29 @@ def random_encoder_state_dict(seed: int = REF_SEED, bf16_exact: bool = True) -> 
     return sd
 
 
+OUTLIER_CHANNELS = (37, 412, 700)
+
+
+def outlier_encoder_state_dict(seed: int = REF_SEED + 7, scale: float = 50.0) -> dict:
+    """Seeded ViT-B/16 weights with the activation statistics real CLIP / GIT towers have and benign random weights lack:
+    a few MASSIVE residual channels (rows ``OUTLIER_CHANNELS`` of ``mlp.fc2`` in layers 2-5 scaled by ``scale``: the fp32
+    residual stream then carries values two orders of magnitude above the rest through every later LayerNorm), heavy-tailed
+    LayerNorm gains (log-normal, a few channels at 3-5x) and matrices that are NOT bf16-representable (the upload rounds
+    them, as it would a real checkpoint).  Used by the parity stress tests only."""
+    sd = random_encoder_state_dict(seed, bf16_exact=False)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed + 1)
+    ch = torch.tensor(OUTLIER_CHANNELS)
+    for l in range(2, 6):
+        p = f"vision_model.encoder.layers.{l}.mlp.fc2."
+        sd[p + "weight"][ch] *= scale
+        sd[p + "bias"][ch] *= scale
+    for name in sd:
+        if name.endswith(("layer_norm1.weight", "layer_norm2.weight", "post_layernorm.weight", "pre_layrnorm.weight")):
+            sd[name] = torch.exp(0.5 * torch.randn(sd[name].shape, generator=g)).contiguous()
+    return sd
+
+
 def random_projection_state_dict(seed: int = REF_SEED + 1, bf16_exact: bool = True) -> dict:
     """Seeded weights of GIT's ``visual_projection`` (HF ``GitProjection``: Linear(768, 768) + LayerNorm) under its
     own key names; the matrix is bf16-representable like the encoder matrices."""

@@ -1,8 +1,8 @@
 """The synthetic suite of BASELINE.json's north star ("identical frame indices on the synthetic suite"): whole clips
 through the GPU path and through the CPU oracle (fp32 encoder restatement pinned to HF + the restated sampler pinned
-to the reference's own function), compared pick by pick.  pytest -m gpu; SASVQA_SUITE_CLIPS (default 6) sets how many
-scene-structured 128-frame clips are run (SASVQA_SUITE_FRAMES=512 switches to BASELINE config 4's long clips and K = 32) -- the oracle's encoder costs ~4 s of host time per clip, so the default
-stays within the test budget and larger runs are recorded under profiles/ (summary JSON written to gpurun_out/).
+to the reference's own function), compared pick by pick.  pytest -m gpu; the default is 16 scene-structured 128-frame
+clips plus 2 clips of 512 frames (BASELINE config 4, K = 32); larger runs (SASVQA_SUITE_CLIPS / SASVQA_SUITE_LONG_CLIPS) are
+recorded under profiles/ (summary JSON written to gpurun_out/).
 
 Every clip is sampled under four (K, W) settings that share its features: (16, 8) = BASELINE config 2 (always the
 top-K fallback), (16, 4) and (8, 8) (greedy path), (16, -1) (adaptive window).  A mismatch is excused only if the
@@ -39,55 +39,83 @@ class _CachedFeatures:
         return type("O", (), {"last_hidden_state": out})()
 
 
+def _run_suite(n_clips, T, settings, enc, oracle_cpu, oracle_gpu, summary, cpu_checked_clips):
+    """n_clips scene-structured clips of T frames through the GPU path and the fp32 oracle.  The oracle's encoder runs on
+    the host for the first `cpu_checked_clips` clips (the pinned CPU restatement) and, for all clips, as the SAME
+    plain-torch fp32 code on the device with TF32 off -- the two are compared where both exist, which is what allows a
+    suite of this size inside the test budget (the host needs ~4 s per 128-frame clip)."""
+    for c in range(n_clips):
+        clip = synth.make_clip(1000 + c, T)
+        frames = vit.image_processor_224(clip)
+        gpu_clip = clip.unsqueeze(0).cuda()
+        with torch.no_grad():
+            fr_dev = vit.image_processor_224(gpu_clip[0])
+            hidden = torch.cat([oracle_gpu(fr_dev[i:i + 64]).last_hidden_state for i in range(0, T, 64)]).cpu()
+            if c < cpu_checked_clips:
+                hidden_cpu = torch.cat([oracle_cpu(frames[i:i + 32]).last_hidden_state for i in range(0, T, 32)])
+                f_a = torch.nn.functional.normalize(hidden.mean(dim=1))
+                f_b = torch.nn.functional.normalize(hidden_cpu.mean(dim=1))
+                drift = (f_a - f_b).abs().max().item()
+                summary["max_oracle_gpu_vs_cpu_feature_diff"] = max(summary["max_oracle_gpu_vs_cpu_feature_diff"], drift)
+                assert drift <= 2e-5, f"fp32 oracle on the device drifted from the CPU oracle: {drift}"
+                hidden = hidden_cpu                                   # where the CPU oracle exists it IS the judge
+        for K, W in settings:
+            res = sas.sample_mdf_batch(gpu_clip, enc, K, W, want_aux=True)
+            _, aux = mdf.sample_representative_frames(frames, _CachedFeatures(hidden), K, W, {"Failure": 0, "Zeros": 0},
+                                                      return_aux=True)
+            lcl_ref = aux["lcl_avg"]
+            eps = (res["lcl_avg"][0].cpu() - lcl_ref).abs().max().item()
+            cos = (res["feats"][0].cpu() * aux["feats"]).sum(dim=1).min().item()
+            got, want = res["indices"][0].cpu().tolist(), list(aux["indices"])
+            assert eps <= 1e-3 and cos >= 0.9999, (c, K, W, eps, cos)
+            key = f"T{T}_K{K}_W{W}"
+            st = summary["per_setting"].setdefault(key, {"picks": 0, "identical": 0, "excused": 0, "fallback_clips": 0,
+                                                         "fallback_zero_border_clips": 0})
+            st["fallback_clips"] += int(aux["status"] == 1)
+            Wr = T // 20 if W == -1 else W
+            st["fallback_zero_border_clips"] += int(aux["status"] == 1 and any(g < Wr or g >= T - Wr for g in got))
+            summary["status_mismatches"] += int(int(res["status"][0]) != aux["status"])
+            for a, b in zip(got, want):
+                st["picks"] += 1
+                summary["picks"] += 1
+                if a == b:
+                    st["identical"] += 1
+                    summary["identical"] += 1
+                else:
+                    assert abs(float(lcl_ref[a]) - float(lcl_ref[b])) <= 2 * eps, (c, K, W, got, want, eps)
+                    st["excused"] += 1
+                    summary["excused"] += 1
+            summary["max_eps"] = max(summary["max_eps"], eps)
+            summary["min_feature_cosine"] = min(summary["min_feature_cosine"], cos)
+
+
 def test_synthetic_suite_indices_identical():
-    n_clips = int(os.environ.get("SASVQA_SUITE_CLIPS", "6"))
-    T = int(os.environ.get("SASVQA_SUITE_FRAMES", "128"))                   # 512 = BASELINE config 4 (long video)
-    settings = SETTINGS if T <= 128 else [(32, 8), (16, 8), (32, -1)]
+    """Default (what the driver runs): 16 clips x 128 frames under four (K, W) settings + 2 clips x 512 frames (BASELINE
+    config 4) under three = 16*56 + 2*80 = 1056 picks.  SASVQA_SUITE_CLIPS / SASVQA_SUITE_LONG_CLIPS scale it."""
+    n_clips = int(os.environ.get("SASVQA_SUITE_CLIPS", "16"))
+    n_long = int(os.environ.get("SASVQA_SUITE_LONG_CLIPS", "2"))
     torch.cuda.set_device(0)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False                      # the device-side oracle is strict fp32
+    torch.backends.cudnn.allow_tf32 = False
     sd = synth.random_encoder_state_dict(synth.REF_SEED)
-    enc = ops.FrameEncoder(sd, chunk_frames=256)
-    oracle_enc = vit.VitOracle(sd)
+    enc = ops.FrameEncoder(sd, chunk_frames=512)
+    oracle_cpu, oracle_gpu = vit.VitOracle(sd), vit.VitOracle(sd, device="cuda")
     torch.set_num_threads(os.cpu_count() or 1)
-    summary = {"clips": n_clips, "frames_per_clip": T, "settings": [list(s) for s in settings], "picks": 0, "identical": 0,
-               "excused": 0, "max_eps": 0.0, "min_feature_cosine": 1.0, "status_mismatches": 0, "per_setting": {}}
+    summary = {"clips_T128": n_clips, "clips_T512": n_long, "picks": 0, "identical": 0, "excused": 0, "max_eps": 0.0,
+               "min_feature_cosine": 1.0, "status_mismatches": 0, "max_oracle_gpu_vs_cpu_feature_diff": 0.0, "per_setting": {}}
     try:
-        for c in range(n_clips):
-            clip = synth.make_clip(1000 + c, T)
-            frames = vit.image_processor_224(clip)
-            with torch.no_grad():
-                hidden = torch.cat([oracle_enc(frames[i:i + 32]).last_hidden_state for i in range(0, T, 32)])
-            gpu_clip = clip.unsqueeze(0).cuda()
-            for K, W in settings:
-                res = sas.sample_mdf_batch(gpu_clip, enc, K, W, want_aux=True)
-                _, aux = mdf.sample_representative_frames(frames, _CachedFeatures(hidden), K, W, {"Failure": 0, "Zeros": 0},
-                                                          return_aux=True)
-                lcl_ref = aux["lcl_avg"]
-                eps = (res["lcl_avg"][0].cpu() - lcl_ref).abs().max().item()
-                cos = (res["feats"][0].cpu() * aux["feats"]).sum(dim=1).min().item()
-                got, want = res["indices"][0].cpu().tolist(), list(aux["indices"])
-                assert eps <= 1e-3 and cos >= 0.9999, (c, K, W, eps, cos)
-                key = f"K{K}_W{W}"
-                st = summary["per_setting"].setdefault(key, {"picks": 0, "identical": 0, "excused": 0, "fallback_clips": 0})
-                st["fallback_clips"] += int(aux["status"] == 1)
-                summary["status_mismatches"] += int(int(res["status"][0]) != aux["status"])
-                for a, b in zip(got, want):
-                    st["picks"] += 1
-                    summary["picks"] += 1
-                    if a == b:
-                        st["identical"] += 1
-                        summary["identical"] += 1
-                    else:
-                        assert abs(float(lcl_ref[a]) - float(lcl_ref[b])) <= 2 * eps, (c, K, W, got, want, eps)
-                        st["excused"] += 1
-                        summary["excused"] += 1
-                summary["max_eps"] = max(summary["max_eps"], eps)
-                summary["min_feature_cosine"] = min(summary["min_feature_cosine"], cos)
+        _run_suite(n_clips, 128, SETTINGS, enc, oracle_cpu, oracle_gpu, summary, cpu_checked_clips=2)
+        _run_suite(n_long, 512, [(32, 8), (16, 8), (32, -1)], enc, oracle_cpu, oracle_gpu, summary, cpu_checked_clips=1)
     finally:
         enc.close()
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    summary["excused_fraction"] = summary["excused"] / max(summary["picks"], 1)
     print("synthetic suite:", json.dumps(summary))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
-        with open(os.path.join(out_dir, f"parity_suite_{n_clips}clips{'' if T == 128 else '_T%d' % T}.json"), "w") as f:
+        with open(os.path.join(out_dir, f"parity_suite_{n_clips}x128_{n_long}x512.json"), "w") as f:
             json.dump(summary, f, indent=1)
     assert summary["status_mismatches"] == 0
-    assert summary["excused"] <= max(2, summary["picks"] // 20), summary           # ties within tolerance stay rare (measured 0.7 % at T=128, 2.5 % at T=512)
+    # ties within tolerance stay rare: measured 0.7 % at T=128 and 2.5 % at T=512 in round 1 -> 1.5 % over this mix
+    assert summary["excused"] <= 0.015 * summary["picks"], summary
