@@ -622,7 +622,8 @@ def run_ours(args):
 
         def e2e_step():
             if args.kind == "mdf-ragged":
-                out = ops.mdf_sample_ragged_host(enc, host_frames, ragged_lengths[:n_e2e], K, W)
+                out = ops.mdf_sample_ragged_host(enc, host_frames, ragged_lengths[:n_e2e], K, W, idx_out=idx_h[:n_e2e],
+                                                 status_out=st_h[:n_e2e], frames_out=fr_h[:n_e2e])
             elif args.kind == "mif":
                 out = sas.sample_mif_host(host_clips, enc, q_h, K, args.ds_rate, idx_out=idx_h, frames_out=fr_h, want_frames=True)
             else:
