@@ -498,7 +498,16 @@ def run_ours(args):
     enc.profile_enable(False)
     launches = ops.launch_count() - launches0
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own time, SM clock under the power cap and joules: the step is the MAX over ranks, so the slowest
+        # piece of silicon on the box sets the number (GPUs differ by 10-15 % in clock at the same 1 kW cap)
+        mine = torch.tensor([elapsed_ms / args.steps, float(clocks["sm_mhz"] or 0.0),
+                             ((j1 - j0) / args.steps) if j0 is not None and j1 is not None else 0.0], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 2) for x in allr], "sm_mhz": [float(x[1]) for x in allr],
+                    "joules_per_step": [round(float(x[2]), 1) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
@@ -687,6 +696,8 @@ def run_ours(args):
             "frames_per_s": value * T, "clocks": clocks, "gpu_launches": int(launches),
             "status_counts": st_counts, "roofline": roofline,
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if sharding_check is not None:
             line["sharding_check"] = sharding_check
         if e2e is not None:
