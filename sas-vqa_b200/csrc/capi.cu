@@ -335,7 +335,15 @@ int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const
 int sasvqa_test_attention_git(const uint16_t* qkv, int n_samples, int n_vis, int L, uint16_t* out, void* stream) {
     return guarded([&]() -> int {
         SASVQA_REQUIRE(n_samples == 0 || (qkv && out), "null argument");
-        return launch_attention_git(CBF(qkv), BF(out), n_samples, n_vis, L, 0, S(stream));
+        SASVQA_REQUIRE(n_vis >= 1 && L >= 0, "the visual prefix must hold at least one token");
+        if (n_samples == 0) return 0;
+        int dev = 0, sms = 148;                                     // the decoder's own sequence: visual rows, then text rows
+        SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
+        SASVQA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (int rc = launch_attention_git_tcgen05(CBF(qkv), BF(out), (long long)n_samples * (n_vis + L), n_samples, n_vis, sms,
+                                                  S(stream)))
+            return rc;
+        return launch_attention_git(CBF(qkv), BF(out), n_samples, n_vis, L, 1, S(stream));
     });
 }
 int sasvqa_test_attention_varlen(const uint16_t* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, uint16_t* out,

@@ -39,12 +39,23 @@ def models(weights):
     enc.close()
 
 
-@pytest.mark.parametrize("n,n_vis,L", [(1, 197, 1), (2, 394, 9), (3, 130, 40), (1, 64, 200)], ids=str)
-def test_git_attention_vs_fp32_reference(n, n_vis, L):
+@pytest.mark.parametrize("n,n_vis,L,ramp", [(1, 197, 1, 0.0), (2, 394, 9, 0.0), (3, 130, 40, 0.0), (1, 64, 200, 0.0),
+                                            (1, 256, 5, 0.0), (2, 1000, 3, 0.0), (2, 3152, 20, 0.0), (1, 3152, 20, 6.0),
+                                            (2, 700, 4, -5.0)], ids=str)
+def test_git_attention_vs_fp32_reference(n, n_vis, L, ramp):
+    """Visual rows: the tcgen05 flash kernel (128-key chunks, tail chunk masked, query tiles that end inside a sample);
+    text rows: the per-row-limit kernel.  ramp != 0 grows (or shrinks) the keys along the sequence so that the running
+    maximum keeps moving by more than the lazy-rescale threshold and the O accumulators in TMEM are rescaled in later
+    chunks (ramp > 0), or is set by the first chunk once and for all (ramp < 0)."""
     torch.manual_seed(n_vis + L)
     S = n_vis + L
     rows = n * S
-    qkv = torch.randn(rows, 2304).to(torch.bfloat16).to(DEV)
+    qkv = torch.randn(rows, 2304)
+    if ramp != 0.0:
+        pos = torch.cat([torch.arange(n_vis).repeat(n), n_vis + torch.arange(L).repeat(n)]).float() / S
+        gain = 1.0 + abs(ramp) * (pos if ramp > 0 else 1.0 - pos)
+        qkv[:, 768:1536] *= gain[:, None]
+    qkv = qkv.to(torch.bfloat16).to(DEV)
     out = torch.empty(rows, 768, dtype=torch.bfloat16, device=DEV)
     _capi.check(_capi.lib().sasvqa_test_attention_git(qkv.data_ptr(), n, n_vis, L, out.data_ptr(),
                                                       torch.cuda.current_stream().cuda_stream), "attention_git")
