@@ -258,6 +258,24 @@ int sasvqa_git_vqa_generate_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const
 int sasvqa_git_vqa_hidden_f32(SasvqaGitDecoder* dec, SasvqaEncoder* enc, const float* frames_chw_dev, int B, int K,
                               const int32_t* input_ids_dev, int L, int n_layers, float* hidden_dev, void* stream);
 
+/* ---- decode front end: NVDEC in front of K0 (src/preprocessing/prefetch_loader.py:57-67) -----------------------------
+ * The reference decodes with cv2 on one host thread: `cap.read()` per frame, BGR -> RGB, keep frame i when i % intv == 0.
+ * Here the GPU's video engine decodes an ELEMENTARY stream held in host memory (H.264 / HEVC Annex B, 8-bit 4:2:0; demux
+ * the container on the host, e.g. `ffmpeg -c copy -bsf:v h264_mp4toannexb`) into device memory, display order:
+ *   format 0: uint8 RGB frames [n, H, W, 3] -- the layout the uint8 entry points above take (K0 resizes any H x W);
+ *   format 1: raw NV12 [n, H * 3 / 2, W] (luma plane, then interleaved chroma rows).
+ * codec: SASVQA_CODEC_*.  sasvqa_video_probe parses without decoding: info_out[0..3] = width, height, frames a decode
+ * with this `intv` returns, frames in the stream.  sasvqa_video_decode needs H, W equal to the probed size and room for
+ * capacity_frames frames; *n_frames_out = frames written.  Returns after the frames are in device memory (`stream` is
+ * synchronised per frame).  Needs libnvcuvid.so.1 (ships with the driver; loaded on first use); SASVQA_ERR_INVALID with
+ * a message when it, or an NVDEC engine, is missing.  Colour: BT.601 limited-range integer matrix, chroma of the co-sited
+ * 2x2 block -- decode is bit-exact by the codec standard, the colour step is unpinned against cv2's swscale path. */
+#define SASVQA_CODEC_H264 4
+#define SASVQA_CODEC_HEVC 8
+int sasvqa_video_probe(const uint8_t* bitstream_host, uint64_t n_bytes, int codec, int intv, int32_t* info_out);
+int sasvqa_video_decode(const uint8_t* bitstream_host, uint64_t n_bytes, int codec, int intv, uint8_t* frames_dev,
+                        int capacity_frames, int H, int W, int format, int32_t* n_frames_out, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------
  * sasvqa_launch_count: kernels launched by this library in this process so far.
  * Profiling: when enabled, CUDA-event pairs bracket every stage launch on its stream;

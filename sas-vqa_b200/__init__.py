@@ -10,6 +10,7 @@ from ._capi import LIB_PATH, SasvqaError  # noqa: F401
 from .extract import generate_h5  # noqa: F401
 from .ops import FrameEncoder, STATUS_EMPTY, STATUS_FALLBACK, STATUS_OK, STATUS_TOO_FEW  # noqa: F401
 from .scorer import CaptionScorer, generate_inds  # noqa: F401
+from .video import decode_video, probe_video  # noqa: F401
 from .vqa import GitDecoder, vqa_generate, vqa_logits, vqa_loss  # noqa: F401
 from .sampler import (  # noqa: F401
     encode_sampled_frames,
@@ -25,6 +26,6 @@ from .sampler import (  # noqa: F401
 )
 
 __all__ = [
-    "CaptionScorer", "FrameEncoder", "GitDecoder", "vqa_generate", "vqa_logits", "vqa_loss", "SasvqaError", "generate_inds", "encode_sampled_frames", "generate_h5", "mif_select", "sample_frame_indices", "sample_frames_uniform",
+    "CaptionScorer", "FrameEncoder", "decode_video", "probe_video", "GitDecoder", "vqa_generate", "vqa_logits", "vqa_loss", "SasvqaError", "generate_inds", "encode_sampled_frames", "generate_h5", "mif_select", "sample_frame_indices", "sample_frames_uniform",
     "sample_mdf_batch", "sample_mdf_host", "sample_mdf_ragged", "sample_mif_batch", "sample_mif_host", "sample_representative_frames", "synth",
 ]

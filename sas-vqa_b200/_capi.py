@@ -63,6 +63,8 @@ SIGNATURES = {
     "sasvqa_git_vqa_hidden_f32": (c_int, [_p, _p, _p, c_int, c_int, _p, c_int, c_int, _p, _p]),
     "sasvqa_test_attention_git": (c_int, [_p, c_int, c_int, c_int, _p, _p]),
     "sasvqa_test_attention_varlen": (c_int, [_p, _p, c_int, c_int, _p, _p]),
+    "sasvqa_video_probe": (c_int, [_p, c_uint64, c_int, c_int, _p]),
+    "sasvqa_video_decode": (c_int, [_p, c_uint64, c_int, c_int, _p, c_int, c_int, c_int, c_int, _p, _p]),
     "sasvqa_launch_count": (c_int64, []),
     "sasvqa_profile_enable": (c_int, [_p, c_int]),
     "sasvqa_profile_read": (c_int, [_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int]),

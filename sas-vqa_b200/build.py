@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 # development A/B builds: SASVQA_LIB_SUFFIX=_x SASVQA_DEFINES="-DFOO=1" -> libsasvqa_b200_x.so
 SUFFIX = os.environ.get("SASVQA_LIB_SUFFIX", "")
 LIB = os.path.join(HERE, f"libsasvqa_b200{SUFFIX}.so")
-SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu", "attention_git_tcgen05.cu", "elementwise.cu", "select.cu", "resize.cu", "scorer.cu", "git_decoder.cu"]
+SOURCES = ["capi.cu", "encoder.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tcgen05.cu", "attention_git_tcgen05.cu", "elementwise.cu", "select.cu", "resize.cu", "nvdec.cu", "scorer.cu", "git_decoder.cu"]
 # test-only check kernels (CUDA-core GEMM, mma.sync encoder attention): a separate library the product never loads
 TEST_LIB = os.path.join(HERE, "libsasvqa_b200_test.so")
 TEST_SOURCES = ["check/capi_check.cu", "check/gemm_simt.cu", "check/attention_mma_check.cu"]
@@ -54,7 +54,7 @@ def _compile(nvcc: str, sources, lib: str, verbose: bool) -> None:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-lcudart", "-ldl"])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

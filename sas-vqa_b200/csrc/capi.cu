@@ -32,6 +32,8 @@ int visual_tokens(SasvqaEncoder*, const uint8_t*, const float*, int, int, float*
 int mif_sample_device(SasvqaEncoder*, const uint8_t*, const float*, int, int, int, int, const float*, int, int, int32_t*,
                       float*, float*, float*, cudaStream_t);
 
+int video_probe(const uint8_t*, uint64_t, int, int, int32_t*);
+int video_decode(const uint8_t*, uint64_t, int, int, uint8_t*, int, int, int, int, int32_t*, cudaStream_t);
 uint64_t git_decoder_num_params(int, int);
 int git_decoder_create(const float*, uint64_t, int, int, int, SasvqaGitDecoder**);
 void git_decoder_destroy(SasvqaGitDecoder*);
@@ -351,6 +353,17 @@ int sasvqa_test_attention_varlen(const uint16_t* qkv, const int32_t* cu_seqlens,
     return guarded([&]() -> int {
         SASVQA_REQUIRE(n_seqs == 0 || (qkv && cu_seqlens && out), "null argument");
         return launch_attention_varlen(CBF(qkv), BF(out), cu_seqlens, 0, n_seqs, max_len, S(stream));
+    });
+}
+int sasvqa_video_probe(const uint8_t* bitstream_host, uint64_t n_bytes, int codec, int intv, int32_t* info_out) {
+    return guarded([&]() -> int {
+        return video_probe(bitstream_host, n_bytes, codec, intv, info_out);
+    });
+}
+int sasvqa_video_decode(const uint8_t* bitstream_host, uint64_t n_bytes, int codec, int intv, uint8_t* frames_dev, int capacity_frames,
+                        int H, int W, int format, int32_t* n_frames_out, void* stream) {
+    return guarded([&]() -> int {
+        return video_decode(bitstream_host, n_bytes, codec, intv, frames_dev, capacity_frames, H, W, format, n_frames_out, S(stream));
     });
 }
 int sasvqa_test_gemm(const uint16_t* a, const uint16_t* b, int M, int N, int K, int mode, const float* bias_or_pos,
