@@ -12,6 +12,13 @@ Format Specification, version 1.x structures -- what libhdf5 1.6 wrote and every
     fill-value, datatype (IEEE little-endian float32), dataspace (v1, simple, fixed dims) and data-layout
     (v3, contiguous) messages -> raw row-major data, 4 KiB aligned.
 
+OUTPUT CONTRACT: the writer has been checked field by field against the format specification and is read back by this module's
+own reader, by the reference's unmodified ``VideoQADataset`` / ``GITVideoQACollator`` through an ``h5py.File(p, 'r')[name]`` shim
+over that reader (tests/test_consumer_ref.py), and by real h5py wherever h5py is importable (the same test then uses it) -- but
+libhdf5 / h5py are absent from the build image, so a file written HERE has not been opened by libhdf5 itself.  ``writer.py`` uses
+h5py for ``.h5`` paths whenever it is importable and records which backend wrote a file (``SampledFramesWriter.backend_used``); the
+``.npy`` backend is the format tested end to end.
+
 The reader below understands exactly those structures (plus the v1/v2 layout messages and header continuation
 blocks libhdf5 1.6 emitted); tests pin it against a genuine libhdf5-written file that ships with scipy and then
 use it to read what the writer produced.  Rows are exposed as a ``numpy.memmap`` so the extraction loop

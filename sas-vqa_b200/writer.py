@@ -15,6 +15,7 @@
 from __future__ import annotations
 
 import json
+import logging
 import os
 
 import numpy as np
@@ -48,14 +49,18 @@ class SampledFramesWriter:
             self.path = path
             self._fd = h5py.File(path, "w")
             self._ds = self._fd.create_dataset(DATASET, self.shape)          # float32, like the reference
+            self.backend_used = "h5py"
         elif self.backend == "h5":
             self.path = path
             self._fd = None
             self._ds = hdf5_min.create_dataset_file(path, DATASET, self.shape, np.float32)
+            self.backend_used = "hdf5_min (h5py not importable; see the output contract in hdf5_min.py)"
         else:
             self.path = path if path.endswith(".npy") else path + ".npy"
             self._fd = None
             self._ds = np.lib.format.open_memmap(self.path, mode="w+", dtype=np.float32, shape=self.shape)
+            self.backend_used = "npy"
+        logging.getLogger("sasvqa_b200").info("sampled_frames %s -> %s written by %s", self.shape, self.path, self.backend_used)
 
     def __setitem__(self, row, frames) -> None:
         arr = frames.detach().cpu().numpy() if hasattr(frames, "detach") else np.asarray(frames)

@@ -116,3 +116,17 @@ def test_file_is_what_the_reference_reader_expects(ref_consumer, artefacts):
     ds = h5py.File(artefacts["h5"], "r")["sampled_frames"]
     assert tuple(ds.shape) == (N, K, 3 * IMG * IMG) and ds.dtype == np.float32
     np.testing.assert_array_equal(np.asarray(ds[2]), artefacts["rows"][2])
+
+
+def test_real_h5py_opens_the_writers_file(artefacts):
+    """where the real h5py / libhdf5 is installed, it must open a file written by the hand-laid-out writer."""
+    h5py = pytest.importorskip("h5py")
+    if getattr(h5py, "__shim__", None):
+        pytest.skip("only the hdf5_min-backed shim is importable here (no libhdf5 in the image)")
+    from sasvqa_b200 import hdf5_min
+    path = str(artefacts["dir"] / "by_hdf5_min.h5")
+    mm = hdf5_min.create_dataset_file(path, "sampled_frames", artefacts["rows"].shape, np.float32)
+    mm[:] = artefacts["rows"]
+    mm.flush()
+    with h5py.File(path, "r") as f:
+        np.testing.assert_array_equal(np.asarray(f["sampled_frames"]), artefacts["rows"])
