@@ -119,3 +119,61 @@ def test_synthetic_suite_indices_identical():
     assert summary["status_mismatches"] == 0
     # ties within tolerance stay rare: measured 0.7 % at T=128 and 2.5 % at T=512 in round 1 -> 1.5 % over this mix
     assert summary["excused"] <= 0.015 * summary["picks"], summary
+
+
+def test_full_size_c2_batch_indices_vs_oracle():
+    """BASELINE configs[1] at its FULL size -- 256 clips x 128 frames, K = 16, W = 8, one library call -- against the oracle,
+    pick by pick (this shape was only checked through invariants).  The oracle's fp32 encoder runs as the
+    same plain-torch restatement on the device (TF32 off; agreement with the CPU restatement is asserted on two clips), the
+    restated sampler (oracle/mdf.py == utils.py:31-94) on the host.  SASVQA_FULL_C2_CLIPS shrinks it for quick runs."""
+    n_clips = int(os.environ.get("SASVQA_FULL_C2_CLIPS", "256"))
+    T, K, W = 128, 16, 8
+    torch.cuda.set_device(0)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = synth.random_encoder_state_dict(synth.REF_SEED)
+    enc = ops.FrameEncoder(sd, chunk_frames=2048)
+    oracle_cpu, oracle_gpu = vit.VitOracle(sd), vit.VitOracle(sd, device="cuda")
+    torch.set_num_threads(os.cpu_count() or 1)
+    try:
+        clips = synth.make_clips(range(n_clips), T, device="cuda")                  # the bench's own clip ids 0..255
+        res = sas.sample_mdf_batch(clips, enc, K, W, want_aux=True)
+        got_idx, got_st, got_lcl = res["indices"].cpu(), res["status"].cpu(), res["lcl_avg"].cpu()
+        got_feats = res["feats"].cpu()
+        picks = identical = excused = status_bad = 0
+        max_eps, min_cos = 0.0, 1.0
+        for c in range(n_clips):
+            with torch.no_grad():
+                fr = vit.image_processor_224(clips[c])
+                pooled = torch.cat([oracle_gpu(fr[i:i + 64]).last_hidden_state.mean(dim=1) for i in range(0, T, 64)]).cpu()
+                if c < 2:                                                           # device-side oracle == CPU oracle
+                    ref = oracle_cpu(fr.cpu()).last_hidden_state.mean(dim=1)
+                    assert (torch.nn.functional.normalize(ref) - torch.nn.functional.normalize(pooled)).abs().max().item() <= 2e-5
+            feats = torch.nn.functional.normalize(pooled)                             # utils.py:44-47
+            idx_ref, st_ref, lcl_ref, _ = mdf.mdf_indices_from_feats(feats, K, W)       # utils.py:55-93
+            aux = {"indices": idx_ref, "status": st_ref, "lcl_avg": lcl_ref, "feats": feats}
+            eps = (got_lcl[c] - aux["lcl_avg"]).abs().max().item()
+            cos = (got_feats[c] * aux["feats"]).sum(dim=1).min().item()
+            assert eps <= 1e-3 and cos >= 0.9999, (c, eps, cos)
+            max_eps, min_cos = max(max_eps, eps), min(min_cos, cos)
+            status_bad += int(int(got_st[c]) != aux["status"])
+            for a, b in zip(got_idx[c].tolist(), aux["indices"]):
+                picks += 1
+                if a == b:
+                    identical += 1
+                else:
+                    assert abs(float(aux["lcl_avg"][a]) - float(aux["lcl_avg"][b])) <= 2 * eps, (c, a, b, eps)
+                    excused += 1
+    finally:
+        enc.close()
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    summary = {"clips": n_clips, "frames_per_clip": T, "K": K, "W": W, "picks": picks, "identical": identical, "excused": excused,
+               "status_mismatches": status_bad, "max_eps": max_eps, "min_feature_cosine": min_cos}
+    print("full-size c2:", json.dumps(summary))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"parity_c2_full_{n_clips}clips.json"), "w") as f:
+            json.dump(summary, f, indent=1)
+    assert status_bad == 0
+    assert excused <= 0.015 * picks, summary
