@@ -108,8 +108,9 @@ def test_all_identical_frames_clip(encoder, K, W, want_status):
 
 
 def test_two_scene_clip_with_exact_ties(encoder):
-    """Two scenes of identical frames: scores tie exactly inside each scene and dip at the cut.  Picks may differ from the
-    oracle only between tied frames; the spacing rule holds; no pick sits on the cut while tied interior frames are left."""
+    """Two scenes of identical frames: every interior score ties (inside AND across the scenes) and dips at the cut.  Picks
+    may differ from the oracle only between tied frames; the spacing rule holds; no pick sits on the cut while tied interior
+    frames are left."""
     T, K, W = 64, 6, 4
     a, b = synth.make_clip(31, 1), synth.make_clip(32, 1)
     clip = torch.cat([a.expand(T // 2, -1, -1, -1), b.expand(T // 2, -1, -1, -1)]).contiguous()
@@ -125,8 +126,8 @@ def test_two_scene_clip_with_exact_ties(encoder):
     assert all(y - x >= W for x, y in zip(srt, srt[1:])), got                      # utils.py:76-88 spacing
     lcl = aux["lcl_avg"]
     assert min(float(lcl[g]) for g in got) >= float(lcl[T // 2 - W + 1:T // 2 + W].min()), "a cut frame beat a tied interior frame"
-    # every stored frame is one of the two images, in the oracle's scene order (ties never cross scenes: their scores differ)
-    assert [g >= T // 2 for g in got] == [w >= T // 2 for w in want]
+    # (interior windows of BOTH scenes hold identical features, so their scores are all (2W - 1)/(2W - 1) = 1 up to rounding:
+    # the tie spans the two scenes, and which scene wins is exactly the kind of difference the tolerance rule excuses)
     assert torch.equal(res["frames"][0].cpu(), frames[torch.tensor(got)])
 
 
