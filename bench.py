@@ -50,7 +50,7 @@ HBM_STAGE_BYTES_PER_FRAME = {
     "attention": 12 * 197 * (2304 * 2 + 768 * 2),        # q|k|v read once, heads written once (12 layers)
 }
 NCU_GEMM_SUMMARY = os.path.join(ROOT, "profiles", "r02", "ncu_gemm.json")      # written by tools/summarize_ncu.py
-GEMM_SOURCES = ("gemm_tcgen05.cu", "common.cuh")                                 # what the capture's hash covers
+GEMM_SOURCES = ("gemm_tcgen05.cu",)                                              # what the capture's hash covers: the kernel's source file
 E2E_PINNED_BYTES_CAP = 9e9                                                        # pinned host memory per rank for the e2e leg
 
 

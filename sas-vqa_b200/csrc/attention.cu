@@ -1,6 +1,7 @@
 // Small attention kernels on bf16 mma.sync.m16n8k16 with fp32 softmax statistics:
-//  * attention_git_kernel     -- the GIT decoder's attention over [visual tokens | text] for the TEXT-ROW passes (sixth
-//                                block of the forward, greedy decoding steps); the full passes run on tcgen05
+//  * attention_git_kernel     -- the GIT decoder's TEXT rows against a per-layer k|v CACHE of the visual rows: the steps of
+//                                incremental greedy decoding (git_decoder.cu: git_vqa_generate).  The forward itself -- visual
+//                                and text query tiles -- runs on tcgen05 (attention_git_tcgen05.cu).
 //  * attention_short_kernel / attention_varlen_kernel -- the MIF caption cross-encoder's (question, caption) pairs
 //                                (~20 tokens; a tcgen05 instruction needs 128 query rows, six times a pair's length)
 // The encoder's per-frame attention is attention_tcgen05.cu.

@@ -1,12 +1,15 @@
 // Attention of the downstream GIT decoder for the VISUAL rows, on tcgen05 tensor cores (sm_100a).
 //
 // MyGitModel.forward builds a combined mask (src/modeling/modeling.py:116-140): a visual row sees the n_vis = K * 197
-// visual rows of its sample and nothing else; text row t sees every visual row and text rows <= t.  The visual rows are
-// 99.4 % of the queries (K = 16: 3152 of 3172), a plain non-causal softmax(Q K^T / 8) V over n_vis keys -- this kernel;
-// the few text rows keep the per-row-limit mma.sync kernel of attention.cu (20 rows per sample cannot fill an M = 128 UMMA).
+// visual rows of its sample and nothing else; text row t sees every visual row and text rows <= t.  Both are "keys
+// [0, limit(row))".  Visual query tiles (99.4 % of the queries at K = 16: 3152 of 3172) run a plain non-causal
+// softmax(Q K^T / 8) V over the n_vis keys; the text rows of a sample are ONE more query tile per 128 positions whose
+// key chunks are the visual chunks followed by the text chunks up to its own, with the causal limit applied per row in
+// those last chunks (a 20-row text tile fills 16 % of the M = 128 UMMA -- accepted, it is 0.6 % of the work, and it keeps
+// the whole forward on tcgen05).  Incremental decoding against a k|v cache stays on attention.cu's mma.sync kernel.
 //
-// qkv [rows, 2304] bf16 (q | k | v, 12 heads x 64), rows stored visual-first: sample s owns rows [s*n_vis, (s+1)*n_vis).
-// out [rows, 768] bf16.  HF GitSelfAttention, transformers modeling_git.py:202-280.
+// qkv [rows, 2304] bf16 (q | k | v, 12 heads x 64), rows stored visual-first: sample s owns rows [s*n_vis, (s+1)*n_vis)
+// and [n*n_vis + s*L, n*n_vis + (s+1)*L).  out [rows, 768] bf16.  HF GitSelfAttention, transformers modeling_git.py:202-280.
 //
 // Flash attention with the accumulators in TMEM.  Persistent CTAs of 256 threads, TWO per SM (each allocates 256 of the
 // 512 TMEM columns; while one CTA's softmax runs the other's MMAs have the tensor pipe).  One work item = (sample, head,
@@ -91,7 +94,8 @@ __device__ __forceinline__ float git_exp_and_store(const uint32_t (&v)[GK_CHUNK]
 
 __global__ void __launch_bounds__(G_THREADS, 2)
 attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out,
-                             __nv_bfloat16* __restrict__ out, int n_vis, int n_qtiles, int n_chunks, int n_items) {
+                             __nv_bfloat16* __restrict__ out, int n_vis, int L, long long txt_row0, int n_qtiles_vis,
+                             int n_qtiles_txt, int n_chunks_vis, int n_items) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = smem_base;
@@ -131,11 +135,31 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    auto item_coords = [&](int item, int& smp, int& head, int& qt) {
-        qt = item % n_qtiles;
+    // work item -> (sample, head, query tile); tiles [0, n_qtiles_vis) are visual, the rest text tiles.  A tile's key chunks
+    // are the n_chunks_vis visual chunks, then (text tiles) the text chunks 0..tq.
+    struct Item {
+        int smp, head, qt;        // qt < n_qtiles_vis: visual tile qt; else text tile qt - n_qtiles_vis
+        bool text;
+        int tq, n_chunks;
+        long long q_row, vis_row0, txt_base;
+    };
+    const int n_qtiles = n_qtiles_vis + n_qtiles_txt;
+    auto item_coords = [&](int item) {
+        Item t;
+        t.qt = item % n_qtiles;
         const int sh = item / n_qtiles;
-        head = sh % kHeads;
-        smp = sh / kHeads;
+        t.head = sh % kHeads;
+        t.smp = sh / kHeads;
+        t.text = t.qt >= n_qtiles_vis;
+        t.tq = t.text ? t.qt - n_qtiles_vis : 0;
+        t.vis_row0 = (long long)t.smp * n_vis;
+        t.txt_base = txt_row0 + (long long)t.smp * L;
+        t.q_row = t.text ? t.txt_base + (long long)t.tq * GQ_TILE : t.vis_row0 + (long long)t.qt * GQ_TILE;
+        t.n_chunks = n_chunks_vis + (t.text ? t.tq + 1 : 0);
+        return t;
+    };
+    auto chunk_row = [&](const Item& t, int c) -> int {
+        return (int)(c < n_chunks_vis ? t.vis_row0 + (long long)c * GK_CHUNK : t.txt_base + (long long)(c - n_chunks_vis) * GK_CHUNK);
     };
 
     if (warp < 4) {
@@ -144,24 +168,23 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
             // ===================== TMA producer =====================
             uint32_t it = 0, kv_it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                int smp, head, qt;
-                item_coords(item, smp, head, qt);
-                const int row0 = smp * n_vis;
+                const Item t = item_coords(item);
                 mbar_wait(q_empty, (it & 1u) ^ 1u);
                 mbar_arrive_expect_tx(q_full, G_TILE_BYTES);
-                tma_load_2d(q_smem, &map_qkv, head * kHeadDim, row0 + qt * GQ_TILE, q_full);
-                for (int c = 0; c < n_chunks; ++c, ++kv_it) {
+                tma_load_2d(q_smem, &map_qkv, t.head * kHeadDim, (int)t.q_row, q_full);
+                for (int c = 0; c < t.n_chunks; ++c, ++kv_it) {
                     const int st = (int)(kv_it % G_KV_STAGES);
                     mbar_wait(kv_empty(st), ((kv_it / G_KV_STAGES) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(kv_full(st), 2 * G_TILE_BYTES);
-                    tma_load_2d(k_smem(st), &map_qkv, kHidden + head * kHeadDim, row0 + c * GK_CHUNK, kv_full(st));
-                    tma_load_2d(v_smem(st), &map_qkv, 2 * kHidden + head * kHeadDim, row0 + c * GK_CHUNK, kv_full(st));
+                    tma_load_2d(k_smem(st), &map_qkv, kHidden + t.head * kHeadDim, chunk_row(t, c), kv_full(st));
+                    tma_load_2d(v_smem(st), &map_qkv, 2 * kHidden + t.head * kHeadDim, chunk_row(t, c), kv_full(st));
                 }
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
             uint32_t it = 0, kv_it = 0, ch = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int n_chunks = item_coords(item).n_chunks;
                 mbar_wait(q_full, it & 1u);
                 const uint64_t adesc = desc_sw128(q_smem, 0);
                 for (int c = 0; c < n_chunks; ++c, ++kv_it, ++ch) {
@@ -195,11 +218,16 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
         const uint32_t slab = slab_base + (uint32_t)(quarter * G_SLAB_BYTES);
         uint32_t it = 0, ch = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            int smp, head, qt;
-            item_coords(item, smp, head, qt);
+            const Item t = item_coords(item);
+            const int smp = t.smp, head = t.head;
+            // position of this thread's query inside the text (text tiles; rows past L compute on garbage and are never stored)
+            const int txt_pos = min(t.tq * GQ_TILE + quarter * 32 + lane, L - 1);
             float m_ref = -INFINITY, l = 0.f;
-            for (int c = 0; c < n_chunks; ++c, ++ch) {
-                const int nvalid = min(GK_CHUNK, n_vis - c * GK_CHUNK);
+            for (int c = 0; c < t.n_chunks; ++c, ++ch) {
+                // keys [0, limit) of this chunk are visible to this row: the tail of the visual keys, or the causal limit
+                const int limit = c < n_chunks_vis ? min(GK_CHUNK, n_vis - c * GK_CHUNK)
+                                             : min(GK_CHUNK, txt_pos - (c - n_chunks_vis) * GK_CHUNK + 1);
+                const bool full = __all_sync(0xffffffffu, limit == GK_CHUNK);        // warp-uniform: the unmasked fast path
                 mbar_wait(s_full, ch & 1u);
                 tcgen05_fence_after();
                 uint32_t v[GK_CHUNK];
@@ -209,7 +237,7 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                 tmem_ld32(trow + 96u, v + 96);
                 tmem_wait_ld();
                 float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                if (nvalid == GK_CHUNK) {
+                if (full) {
 #pragma unroll
                     for (int j = 0; j < GK_CHUNK; j += 8)
 #pragma unroll
@@ -218,7 +246,7 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                 } else {
 #pragma unroll
                     for (int j = 0; j < GK_CHUNK; ++j)
-                        if (j < nvalid) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(v[j]));
+                        if (j < limit) mx[j & 3] = fmaxf(mx[j & 3], __uint_as_float(v[j]));
                 }
                 const float cmax = max3(mx[0], mx[1], fmaxf(mx[2], mx[3])) * kGitScaleLog2e;
                 // move the reference maximum only when it is more than 2^8 behind (always on the first chunk: ref = -inf)
@@ -240,8 +268,7 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                         }
                     }
                 }
-                l += nvalid == GK_CHUNK ? git_exp_and_store<false>(v, m_ref, nvalid, trow)
-                                        : git_exp_and_store<true>(v, m_ref, nvalid, trow);
+                l += full ? git_exp_and_store<false>(v, m_ref, limit, trow) : git_exp_and_store<true>(v, m_ref, limit, trow);
                 tmem_wait_st();
                 tcgen05_fence_before();
                 mbar_arrive(p_full);
@@ -249,8 +276,8 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
             // ---- epilogue: this warp's 32 query rows of this head
             mbar_wait(o_full, it & 1u);
             tcgen05_fence_after();
-            const int row_in_sample = qt * GQ_TILE + quarter * 32;
-            const int rows_valid = n_vis - row_in_sample;                          // <= 0: the whole slab is past the sample
+            const int row_in_sample = (t.text ? t.tq : t.qt) * GQ_TILE + quarter * 32;
+            const int rows_valid = (t.text ? L : n_vis) - row_in_sample;           // <= 0: the whole slab is past the sample
             const float inv_l = 1.0f / l;
             uint32_t w[32];
 #pragma unroll
@@ -264,7 +291,7 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                     w[16 * half + j] = pack_bf16x2((__uint_as_float(oa[2 * j]) + __uint_as_float(ob[2 * j])) * inv_l,
                                                    (__uint_as_float(oa[2 * j + 1]) + __uint_as_float(ob[2 * j + 1])) * inv_l);
             }
-            const long long grow = (long long)smp * n_vis + row_in_sample;          // global row of this warp's first query
+            const long long grow = t.q_row + quarter * 32;                           // global row of this warp's first query
             if (rows_valid >= 32) {
                 if (lane == 0) bulk_wait_read_all();                                 // the store that last read this slab is done
                 __syncwarp();
@@ -297,23 +324,30 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
 
 }  // namespace
 
-// Visual-row attention of one group: qkv / out hold `rows_total` rows (n_samples * n_vis visual rows first).
+// Attention of one group of n_samples sequences: qkv / out hold `rows_total` rows (n_samples * n_vis visual rows first, then
+// n_samples * L text rows).  include_visual = 0: only the text rows are queries (the last block when nobody reads the
+// visual rows afterwards); L = 0: visual rows only (the prefill of incremental decoding).
 int launch_attention_git_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, long long rows_total, int n_samples, int n_vis,
-                                 int num_sms, cudaStream_t s) {
+                                 int L, int include_visual, int num_sms, cudaStream_t s) {
     if (n_samples == 0) return 0;
-    SASVQA_REQUIRE(n_vis >= 1 && rows_total >= (long long)n_samples * n_vis, "bad visual row count");
+    SASVQA_REQUIRE(n_vis >= 1 && L >= 0 && rows_total >= (long long)n_samples * (n_vis + L), "bad row counts");
+    SASVQA_REQUIRE(rows_total < 2147483647LL, "too many rows for one launch");
     SASVQA_REQUIRE(((uintptr_t)qkv & 127) == 0 && ((uintptr_t)out & 127) == 0, "unaligned attention buffers");
+    const int n_qtiles_vis = include_visual ? (n_vis + GQ_TILE - 1) / GQ_TILE : 0;
+    const int n_qtiles_txt = (L + GQ_TILE - 1) / GQ_TILE;
+    const int n_chunks_vis = (n_vis + GK_CHUNK - 1) / GK_CHUNK;
+    const long long n_items = (long long)n_samples * kHeads * (n_qtiles_vis + n_qtiles_txt);
+    if (n_items == 0) return 0;
+    SASVQA_REQUIRE(n_items < 2147483647LL, "too many attention work items for one launch");
     CUtensorMap map_qkv, map_out;
     int rc = make_tensor_map_bf16_kmajor(&map_qkv, qkv, (uint64_t)rows_total, kQkv, 128);
     if (rc) return rc;
     if ((rc = make_tensor_map_out(&map_out, out, (uint64_t)rows_total, kHidden, 0))) return rc;
     static SmemAttrCache smem_attr;
     if ((rc = smem_attr.ensure(attention_git_tcgen05_kernel, G_SMEM))) return rc;
-    const int n_qtiles = (n_vis + GQ_TILE - 1) / GQ_TILE, n_chunks = (n_vis + GK_CHUNK - 1) / GK_CHUNK;
-    const long long n_items = (long long)n_samples * kHeads * n_qtiles;
-    SASVQA_REQUIRE(n_items < 2147483647LL, "too many attention work items for one launch");
     const int grid = (int)std::min<long long>(n_items, 2LL * num_sms);
-    attention_git_tcgen05_kernel<<<grid, G_THREADS, G_SMEM, s>>>(map_qkv, map_out, out, n_vis, n_qtiles, n_chunks, (int)n_items);
+    attention_git_tcgen05_kernel<<<grid, G_THREADS, G_SMEM, s>>>(map_qkv, map_out, out, n_vis, L, (long long)n_samples * n_vis,
+                                                                 n_qtiles_vis, n_qtiles_txt, n_chunks_vis, (int)n_items);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return 0;

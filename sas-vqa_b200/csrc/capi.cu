@@ -342,10 +342,8 @@ int sasvqa_test_attention_git(const uint16_t* qkv, int n_samples, int n_vis, int
         int dev = 0, sms = 148;                                     // the decoder's own sequence: visual rows, then text rows
         SASVQA_CUDA_CHECK(cudaGetDevice(&dev));
         SASVQA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (int rc = launch_attention_git_tcgen05(CBF(qkv), BF(out), (long long)n_samples * (n_vis + L), n_samples, n_vis, sms,
-                                                  S(stream)))
-            return rc;
-        return launch_attention_git(CBF(qkv), BF(out), n_samples, n_vis, L, 1, S(stream));
+        return launch_attention_git_tcgen05(CBF(qkv), BF(out), (long long)n_samples * (n_vis + L), n_samples, n_vis, L, 1, sms,
+                                            S(stream));
     });
 }
 int sasvqa_test_attention_varlen(const uint16_t* qkv, const int32_t* cu_seqlens, int n_seqs, int max_len, uint16_t* out,

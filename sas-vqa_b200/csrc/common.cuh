@@ -148,9 +148,9 @@ int launch_attention_varlen(const __nv_bfloat16* qkv, __nv_bfloat16* out, const 
                             int n_seqs, int max_len, cudaStream_t s);
 int launch_attention_git(const __nv_bfloat16* qkv, __nv_bfloat16* out, int n_samples, int n_vis, int L, int text_only,
                          cudaStream_t s, const __nv_bfloat16* vis_kv = nullptr);
-// the visual rows of the same attention on tcgen05 (attention_git_tcgen05.cu); text rows: launch_attention_git(text_only = 1)
+// the same attention on tcgen05 (attention_git_tcgen05.cu): visual query tiles (include_visual) + one text tile per 128 positions
 int launch_attention_git_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, long long rows_total, int n_samples, int n_vis,
-                                 int num_sms, cudaStream_t s);
+                                 int L, int include_visual, int num_sms, cudaStream_t s);
 int launch_layernorm_post(float* x, __nv_bfloat16* h, long long rows, const float* gamma, const float* beta, float eps,
                           cudaStream_t s);
 int launch_embed_layernorm(const int32_t* ids, const int32_t* type_ids, const int32_t* cu_seqlens, int row_base,

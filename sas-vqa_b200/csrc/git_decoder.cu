@@ -470,9 +470,8 @@ int git_vqa_logits(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frames,
             g.A = d->h; g.B = Ly.w_qkv; g.M = (int)M; g.N = kQkv; g.K = kHidden;
             g.epilogue = EPI_BIAS_BF16; g.bias = Ly.b_qkv; g.out_bf16 = d->big;
             if ((rc = dgemm(d, g, &d->m_h, &Ly.m_qkv, &d->m_out_qkv, s))) return rc;
-            // visual rows (99 % of the queries): flash attention on tcgen05; text rows: the per-row-limit kernel
-            if (!text_only && (rc = launch_attention_git_tcgen05(d->big, d->h, M, n, n_vis, d->num_sms, s))) return rc;
-            if ((rc = launch_attention_git(d->big, d->h, n, n_vis, L, 1, s))) return rc;
+            // flash attention on tcgen05: the visual query tiles (skipped in the text-only block) and one text tile per sample
+            if ((rc = launch_attention_git_tcgen05(d->big, d->h, M, n, n_vis, L, text_only ? 0 : 1, d->num_sms, s))) return rc;
             g = GemmArgs{};
             g.A = hr; g.B = Ly.w_out; g.M = (int)Mr; g.N = kHidden; g.K = kHidden;
             g.epilogue = EPI_BIAS_RESID_F32; g.bias = Ly.b_out; g.out_f32 = xr;
@@ -600,7 +599,7 @@ int git_vqa_generate(SasvqaGitDecoder* d, SasvqaEncoder* enc, const float* frame
                                                     kQkv * sizeof(__nv_bfloat16), 2 * kHidden * sizeof(__nv_bfloat16),
                                                     (size_t)rows_vis, cudaMemcpyDeviceToDevice, s));
                 if (last) return -1;                            // nobody reads the visual rows after the last block
-                return launch_attention_git_tcgen05(d->big, d->h, rows_vis, n, n_vis, d->num_sms, s);
+                return launch_attention_git_tcgen05(d->big, d->h, rows_vis, n, n_vis, 0, 1, d->num_sms, s);
             };
             if ((rc = run_block(d, d->L[l], rows_vis, att, s))) return rc;
         }

@@ -35,7 +35,7 @@ def gemm_json(rep, out_path, chunk_frames, capture):
     import hashlib, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     h = hashlib.sha256()
-    for name in ("gemm_tcgen05.cu", "common.cuh"):
+    for name in ("gemm_tcgen05.cu",):
         h.update(open(os.path.join(root, "sas-vqa_b200", "csrc", name), "rb").read())
     wanted = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
               "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
@@ -62,7 +62,7 @@ def gemm_json(rep, out_path, chunk_frames, capture):
     if resid:
         modes["out_proj"], modes["fc2"] = resid[0], resid[-1]
     assert set(modes) == {"qkv", "out_proj", "fc1", "fc2"}, modes.keys()
-    out = {"source_sha256_16": h.hexdigest()[:16], "sources": ["gemm_tcgen05.cu", "common.cuh"], "chunk_frames": chunk_frames,
+    out = {"source_sha256_16": h.hexdigest()[:16], "sources": ["gemm_tcgen05.cu"], "chunk_frames": chunk_frames,
            "capture": capture, "modes": modes,
            "mean_dram_bytes_per_launch": sum(m["dram_bytes"] for m in modes.values()) / 4,
            "note": "one launch per mode from `ncu --set full --clock-control none` (cold-cache, serialised: shares agree with the live "
