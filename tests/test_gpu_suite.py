@@ -125,9 +125,12 @@ def test_full_size_c2_batch_indices_vs_oracle():
     """BASELINE configs[1] at its FULL size -- 256 clips x 128 frames, K = 16, W = 8, one library call -- against the oracle,
     pick by pick (this shape was only checked through invariants).  The oracle's fp32 encoder runs as the
     same plain-torch restatement on the device (TF32 off; agreement with the CPU restatement is asserted on two clips), the
-    restated sampler (oracle/mdf.py == utils.py:31-94) on the host.  SASVQA_FULL_C2_CLIPS shrinks it for quick runs."""
-    n_clips = int(os.environ.get("SASVQA_FULL_C2_CLIPS", "256"))
-    T, K, W = 128, 16, 8
+    restated sampler (oracle/mdf.py == utils.py:31-94) on the host.  SASVQA_FULL_SHAPE = c3 | c4 runs the other full-size
+    BASELINE configs the same way (c3: MIF on synthetic question embeddings, K = 8; c4: 64 clips x 512 frames, K = 32) --
+    recorded under profiles/, not part of the default run; SASVQA_FULL_C2_CLIPS shrinks the clip count for quick runs."""
+    shape = os.environ.get("SASVQA_FULL_SHAPE", "c2")
+    n_default, T, K, W = {"c2": (256, 128, 16, 8), "c3": (256, 128, 8, 0), "c4": (64, 512, 32, 8)}[shape]
+    n_clips = int(os.environ.get("SASVQA_FULL_C2_CLIPS", str(n_default)))
     torch.cuda.set_device(0)
     tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -137,43 +140,68 @@ def test_full_size_c2_batch_indices_vs_oracle():
     oracle_cpu, oracle_gpu = vit.VitOracle(sd), vit.VitOracle(sd, device="cuda")
     torch.set_num_threads(os.cpu_count() or 1)
     try:
-        clips = synth.make_clips(range(n_clips), T, device="cuda")                  # the bench's own clip ids 0..255
-        res = sas.sample_mdf_batch(clips, enc, K, W, want_aux=True)
-        got_idx, got_st, got_lcl = res["indices"].cpu(), res["status"].cpu(), res["lcl_avg"].cpu()
-        got_feats = res["feats"].cpu()
-        picks = identical = excused = status_bad = 0
+        clips = synth.make_clips(range(n_clips), T, device="cuda")                  # the bench's own clip ids
+        if shape == "c3":
+            q = synth.question_embeddings(range(n_clips), device="cuda")
+            res = sas.sample_mif_batch(clips, enc, q, K, 1, want_aux=True)
+            got_lcl, got_st = res["scores"].cpu(), torch.zeros(n_clips, dtype=torch.int32)
+        else:
+            res = sas.sample_mdf_batch(clips, enc, K, W, want_aux=True)
+            got_lcl, got_st = res["lcl_avg"].cpu(), res["status"].cpu()
+        got_idx, got_feats = res["indices"].cpu(), res["feats"].cpu()
+        picks = identical = excused = status_bad = cascade = clips_with_tie = 0
         max_eps, min_cos = 0.0, 1.0
         for c in range(n_clips):
             with torch.no_grad():
                 fr = vit.image_processor_224(clips[c])
                 pooled = torch.cat([oracle_gpu(fr[i:i + 64]).last_hidden_state.mean(dim=1) for i in range(0, T, 64)]).cpu()
-                if c < 2:                                                           # device-side oracle == CPU oracle
+                if c < 2 and T <= 128:                                              # device-side oracle == CPU oracle
                     ref = oracle_cpu(fr.cpu()).last_hidden_state.mean(dim=1)
                     assert (torch.nn.functional.normalize(ref) - torch.nn.functional.normalize(pooled)).abs().max().item() <= 2e-5
             feats = torch.nn.functional.normalize(pooled)                             # utils.py:44-47
-            idx_ref, st_ref, lcl_ref, _ = mdf.mdf_indices_from_feats(feats, K, W)       # utils.py:55-93
+            if shape == "c3":
+                lcl_ref = mdf.mif_scores(feats, q[c].cpu())
+                idx_ref, st_ref = mdf.mif_select(lcl_ref, K, 1), 0                  # gen_sample.py:87-88
+            else:
+                idx_ref, st_ref, lcl_ref, _ = mdf.mdf_indices_from_feats(feats, K, W)   # utils.py:55-93
             aux = {"indices": idx_ref, "status": st_ref, "lcl_avg": lcl_ref, "feats": feats}
             eps = (got_lcl[c] - aux["lcl_avg"]).abs().max().item()
             cos = (got_feats[c] * aux["feats"]).sum(dim=1).min().item()
             assert eps <= 1e-3 and cos >= 0.9999, (c, eps, cos)
             max_eps, min_cos = max(max_eps, eps), min(min_cos, cos)
             status_bad += int(int(got_st[c]) != aux["status"])
+            first = True
             for a, b in zip(got_idx[c].tolist(), aux["indices"]):
                 picks += 1
                 if a == b:
                     identical += 1
-                else:
-                    assert abs(float(aux["lcl_avg"][a]) - float(aux["lcl_avg"][b])) <= 2 * eps, (c, a, b, eps)
+                    continue
+                gap = abs(float(aux["lcl_avg"][a]) - float(aux["lcl_avg"][b]))
+                if first:
+                    # the FIRST pick that differs must be a tie within the tolerance; on the greedy path it changes the
+                    # interval split, so later picks of the clip may differ as its consequence (counted, not excused)
+                    assert gap <= 2 * eps, (c, a, b, gap, eps)
+                    first = False
+                    clips_with_tie += 1
+                if gap <= 2 * eps:
                     excused += 1
+                else:
+                    cascade += 1
     finally:
         enc.close()
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
-    summary = {"clips": n_clips, "frames_per_clip": T, "K": K, "W": W, "picks": picks, "identical": identical, "excused": excused,
+    summary = {"shape": shape, "clips": n_clips, "frames_per_clip": T, "K": K, "W": W, "picks": picks, "identical": identical,
+               "excused": excused, "picks_after_a_tie_changed_the_greedy_split": cascade, "clips_with_a_tie": clips_with_tie,
                "status_mismatches": status_bad, "max_eps": max_eps, "min_feature_cosine": min_cos}
-    print("full-size c2:", json.dumps(summary))
+    print(f"full-size {shape}:", json.dumps(summary))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
-        with open(os.path.join(out_dir, f"parity_c2_full_{n_clips}clips.json"), "w") as f:
+        with open(os.path.join(out_dir, f"parity_{shape}_full_{n_clips}clips.json"), "w") as f:
             json.dump(summary, f, indent=1)
     assert status_bad == 0
-    assert excused <= 0.015 * picks, summary
+    # picks that are not the oracle's, for any reason.  c2 (what the driver runs): measured 0.71 %.  The env-gated shapes tie more
+    # often at the same score error (eps ~ 7e-5): c3's relevance scores <feat, q> differ less from frame to frame (measured 4.2 %
+    # excused), c4's 512-frame clips hold 32 scenes of near-equal frames and a tie changes the greedy split (measured 1.7 %
+    # excused + 3.4 % in its wake, 13 of 64 clips touched) -- all inside the north star's tolerance rule, recorded in profiles/r02
+    bound = {"c2": 0.015, "c3": 0.08, "c4": 0.08}[shape]
+    assert excused + cascade <= bound * picks, summary
