@@ -13,21 +13,23 @@
 //
 // Flash attention with the accumulators in TMEM.  Persistent CTAs of 256 threads, TWO per SM (each allocates 256 of the
 // 512 TMEM columns; while one CTA's softmax runs the other's MMAs have the tensor pipe).  One work item = (sample, head,
-// tile of 128 query rows); its keys stream through shared memory in chunks of 128:
-//   warp 0     TMA: Q tile once per item, K and V chunks double-buffered (128B-swizzled 128 x 64 bf16 tiles)
-//   warp 1     MMA issuer:  S = Q K_c^T        (M=128, N=128, K=64: 4 UMMAs, both operands K-major smem)
+// tile of 128 query rows); its keys stream through shared memory in chunks of 64:
+//   warp 0     TMA: Q tile once per item, K and V chunks through a 4-stage ring (128B-swizzled 64 x 64 bf16 tiles)
+//   warp 1     MMA issuer:  S = Q K_c^T        (M=128, N=64, K=64: 4 UMMAs, both operands K-major smem) into one of TWO S
+//                                               buffers, issued one chunk AHEAD: S of chunk c+1 runs under the softmax of chunk c
 //                           O += P V_c         (A = P from TMEM as packed bf16, B = V chunk as an MN-major smem operand,
-//                                               8 UMMAs of 16 keys alternating between two accumulators O_a / O_b:
+//                                               4 UMMAs of 16 keys alternating between two accumulators O_a / O_b:
 //                                               back-to-back UMMAs into one N=64 accumulator are latency-chained)
-//              MMAs execute in issue order, so S of chunk c+1 may be issued right behind P V of chunk c although P
-//              aliases the S columns.
-//   warps 4-7  online softmax, one thread per query row: the 128 scores are read from TMEM once into registers, the
+//              MMAs execute in issue order, so S of chunk c+2 may be issued behind P V of chunk c although it overwrites
+//              the buffer P of chunk c lives in.
+//   warps 4-7  online softmax, one thread per query row: the 64 scores are read from TMEM once into registers, the
 //              running reference maximum only moves when a chunk's maximum exceeds it by more than 2^8 (then -- rarely
-//              after the first chunks -- the thread rescales its rows of O_a / O_b in TMEM; when S of chunk c is
-//              complete P V of chunk c-1 is too, so O is quiescent), P = exp2(S * scale - ref) goes back as packed bf16
-//              over the consumed columns.  After the last chunk the same warps run the epilogue: (O_a + O_b) / l ->
-//              bf16 -> swizzled smem slab -> one TMA store per 32 rows.
-// TMEM columns: S fp32 [0,128) with P packed over [0,64); O_a [128,192); O_b [192,256).
+//              after the first chunks -- the thread waits for P V of the previous chunk (its own barrier: S of this chunk
+//              was issued before that P V) and rescales its rows of O_a / O_b in TMEM), P = exp2(S * scale - ref) goes
+//              back as packed bf16 over the consumed columns (every 4th pair of exponentials on the FMA pipe).  "P written"
+//              has one barrier per S buffer: a fast warp may be a chunk ahead of a slow one.  After the last chunk the same
+//              warps run the epilogue: (O_a + O_b) / l -> bf16 -> swizzled smem slab -> one TMA store per 32 rows.
+// TMEM columns: S buffers fp32 [0,64) and [64,128), P packed over the first 32 columns of its buffer; O_a [128,192); O_b [192,256).
 #include <algorithm>
 
 #include "tcgen05_util.cuh"
@@ -37,13 +39,14 @@ namespace sasvqa {
 namespace {
 
 constexpr int GQ_TILE = 128;                      // query rows per work item
-constexpr int GK_CHUNK = 128;                     // keys per chunk
-constexpr int G_TILE_BYTES = 128 * 128;           // 128 rows x 64 bf16
-constexpr int G_KV_STAGES = 2;
+constexpr int GK_CHUNK = 64;                      // keys per chunk (two S buffers of 64 TMEM columns: S of chunk c+1 runs under the softmax of chunk c)
+constexpr int G_TILE_BYTES = 128 * 128;           // Q tile: 128 rows x 64 bf16
+constexpr int G_KV_BYTES = GK_CHUNK * 128;        // K or V chunk: 64 rows x 64 bf16
+constexpr int G_KV_STAGES = 4;
 constexpr int G_THREADS = 256;
 constexpr int G_REGS_CTRL = 40, G_REGS_SOFTMAX = 208;     // 128 * (40 + 208) = 31 744 <= 32 768 per CTA (two CTAs per SM)
 constexpr int G_SLAB_BYTES = 32 * 128;
-constexpr int G_SMEM = G_TILE_BYTES * (1 + 2 * G_KV_STAGES) + 4 * G_SLAB_BYTES + 1024 + 256;    // 99 584 B
+constexpr int G_SMEM = G_TILE_BYTES + 2 * G_KV_STAGES * G_KV_BYTES + 4 * G_SLAB_BYTES + 1024 + 256;    // 99 584 B
 constexpr uint32_t G_OA_COL = 128, G_OB_COL = 192, G_TMEM_COLS = 256;
 constexpr float kGitScaleLog2e = 0.125f * 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;         // log2 units: P stays <= 2^8 between two moves of the reference maximum
@@ -54,7 +57,7 @@ constexpr uint32_t kGitIdescS = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 constexpr uint32_t kGitIdescPV = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 #ifndef SASVQA_GIT_POLY_EVERY
-#define SASVQA_GIT_POLY_EVERY 0                   // > 0: every n-th pair of exponentials on the FMA pipe instead of MUFU
+#define SASVQA_GIT_POLY_EVERY 4                   // every 4th pair of exponentials on the FMA pipe instead of MUFU (A/B: 0.760 -> 0.726 ms)
 #endif
 constexpr int kPolyEvery = SASVQA_GIT_POLY_EVERY;
 
@@ -65,7 +68,7 @@ __device__ __forceinline__ float git_exp_and_store(const uint32_t (&v)[GK_CHUNK]
     const uint64_t scale2 = pack_f32x2(kGitScaleLog2e, kGitScaleLog2e), neg_m2 = pack_f32x2(-m_ref, -m_ref);
     uint64_t acc[2] = {0ull, 0ull};
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {                                  // 32 scores -> 16 packed registers -> one TMEM store
+    for (int g = 0; g < GK_CHUNK / 32; ++g) {                      // 32 scores -> 16 packed registers -> one TMEM store
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -93,21 +96,26 @@ __device__ __forceinline__ float git_exp_and_store(const uint32_t (&v)[GK_CHUNK]
 }
 
 __global__ void __launch_bounds__(G_THREADS, 2)
-attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out,
+attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_kv,
+                             const __grid_constant__ CUtensorMap map_out,
                              __nv_bfloat16* __restrict__ out, int n_vis, int L, long long txt_row0, int n_qtiles_vis,
                              int n_qtiles_txt, int n_chunks_vis, int n_items) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = smem_base;
-    auto k_smem = [&](int st) { return smem_base + (uint32_t)((1 + st) * G_TILE_BYTES); };
-    auto v_smem = [&](int st) { return smem_base + (uint32_t)((1 + G_KV_STAGES + st) * G_TILE_BYTES); };
-    const uint32_t slab_base = smem_base + (uint32_t)((1 + 2 * G_KV_STAGES) * G_TILE_BYTES);
+    auto k_smem = [&](int st) { return smem_base + (uint32_t)(G_TILE_BYTES + st * G_KV_BYTES); };
+    auto v_smem = [&](int st) { return smem_base + (uint32_t)(G_TILE_BYTES + (G_KV_STAGES + st) * G_KV_BYTES); };
+    const uint32_t slab_base = smem_base + (uint32_t)(G_TILE_BYTES + 2 * G_KV_STAGES * G_KV_BYTES);
     const uint32_t bar_base = slab_base + 4 * G_SLAB_BYTES;
     const uint32_t q_full = bar_base, q_empty = bar_base + 8;
     auto kv_full = [&](int st) { return bar_base + 8u * (2 + st); };
-    auto kv_empty = [&](int st) { return bar_base + 8u * (4 + st); };
-    const uint32_t s_full = bar_base + 8u * 6, p_full = bar_base + 8u * 7, o_full = bar_base + 8u * 8;
-    const uint32_t tmem_slot = bar_base + 8u * 9;
+    auto kv_empty = [&](int st) { return bar_base + 8u * (2 + G_KV_STAGES + st); };
+    auto s_full = [&](int b) { return bar_base + 8u * (2 + 2 * G_KV_STAGES + b); };       // one per S buffer
+    // one "P written" barrier per S buffer: S of chunk c+1 is ready early, so a fast softmax warp may arrive for chunk c+1 before a
+    // slow one arrived for chunk c -- with a single barrier the two arrivals would complete the same phase
+    auto p_full = [&](int b) { return bar_base + 8u * (4 + 2 * G_KV_STAGES + b); };
+    const uint32_t pv_done = bar_base + 8u * (6 + 2 * G_KV_STAGES), o_full = pv_done + 8u;
+    const uint32_t tmem_slot = pv_done + 16u;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,11 +126,15 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
             mbar_init(kv_full(st), 1);
             mbar_init(kv_empty(st), 1);
         }
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(s_full(0), 1);
+        mbar_init(s_full(1), 1);
+        mbar_init(p_full(0), 128);
+        mbar_init(p_full(1), 128);
+        mbar_init(pv_done, 1);
         mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     }
     if (warp == 1) {
@@ -155,7 +167,7 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
         t.vis_row0 = (long long)t.smp * n_vis;
         t.txt_base = txt_row0 + (long long)t.smp * L;
         t.q_row = t.text ? t.txt_base + (long long)t.tq * GQ_TILE : t.vis_row0 + (long long)t.qt * GQ_TILE;
-        t.n_chunks = n_chunks_vis + (t.text ? t.tq + 1 : 0);
+        t.n_chunks = n_chunks_vis + (t.text ? (t.tq + 1) * (GQ_TILE / GK_CHUNK) : 0);
         return t;
     };
     auto chunk_row = [&](const Item& t, int c) -> int {
@@ -175,37 +187,47 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                 for (int c = 0; c < t.n_chunks; ++c, ++kv_it) {
                     const int st = (int)(kv_it % G_KV_STAGES);
                     mbar_wait(kv_empty(st), ((kv_it / G_KV_STAGES) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(kv_full(st), 2 * G_TILE_BYTES);
-                    tma_load_2d(k_smem(st), &map_qkv, kHidden + t.head * kHeadDim, chunk_row(t, c), kv_full(st));
-                    tma_load_2d(v_smem(st), &map_qkv, 2 * kHidden + t.head * kHeadDim, chunk_row(t, c), kv_full(st));
+                    mbar_arrive_expect_tx(kv_full(st), 2 * G_KV_BYTES);
+                    tma_load_2d(k_smem(st), &map_kv, kHidden + t.head * kHeadDim, chunk_row(t, c), kv_full(st));
+                    tma_load_2d(v_smem(st), &map_kv, 2 * kHidden + t.head * kHeadDim, chunk_row(t, c), kv_full(st));
                 }
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
+            // S of chunk c+1 goes into the OTHER S buffer while the softmax warps work on chunk c (MMAs execute in issue order, so
+            // it is safe behind P V of chunk c-1, the last reader of that buffer); P V of chunk c follows once P is written
             uint32_t it = 0, kv_it = 0, ch = 0;
+            auto issue_s = [&](uint64_t adesc, uint32_t kv_index, uint32_t chunk_index) {
+                const int st = (int)(kv_index % G_KV_STAGES);
+                mbar_wait(kv_full(st), (kv_index / G_KV_STAGES) & 1u);
+                tcgen05_fence_after();
+                const uint64_t bdesc = desc_sw128(k_smem(st), 0);
+                const uint32_t buf = chunk_index & 1u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mma_ss(tmem_base + buf * GK_CHUNK, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kGitIdescS, k != 0);
+                tcgen05_commit(s_full((int)buf));
+            };
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int n_chunks = item_coords(item).n_chunks;
                 mbar_wait(q_full, it & 1u);
                 const uint64_t adesc = desc_sw128(q_smem, 0);
+                issue_s(adesc, kv_it, ch);
                 for (int c = 0; c < n_chunks; ++c, ++kv_it, ++ch) {
+                    if (c + 1 < n_chunks) issue_s(adesc, kv_it + 1, ch + 1);
+                    else tcgen05_commit(q_empty);                            // the item's last scores are issued: Q smem reusable
                     const int st = (int)(kv_it % G_KV_STAGES);
-                    mbar_wait(kv_full(st), (kv_it / G_KV_STAGES) & 1u);
-                    tcgen05_fence_after();
-                    const uint64_t bdesc = desc_sw128(k_smem(st), 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        mma_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kGitIdescS, k != 0);
-                    tcgen05_commit(s_full);
-                    if (c == n_chunks - 1) tcgen05_commit(q_empty);          // the item's last scores: Q smem reusable
-                    mbar_wait(p_full, ch & 1u);                              // softmax wrote P (and rescaled O if needed)
+                    mbar_wait(p_full((int)(ch & 1u)), (ch >> 1) & 1u);       // softmax wrote P (and rescaled O if needed)
                     tcgen05_fence_after();
                     const uint64_t vdesc = desc_sw128(v_smem(st), GK_CHUNK * 128);
+                    const uint32_t pcol = tmem_base + (ch & 1u) * GK_CHUNK;  // P packed over the first half of its S buffer
                     // 16 keys per UMMA = 8 packed-bf16 TMEM columns of P = 2048 B of V; even k-steps -> O_a, odd -> O_b
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        mma_ts(tmem_base + ((j & 1) ? G_OB_COL : G_OA_COL), tmem_base + (uint32_t)(8 * j),
-                               vdesc + (uint64_t)(128 * j), kGitIdescPV, (c != 0 || j >= 2) ? 1u : 0u);
+                    for (int j = 0; j < GK_CHUNK / 16; ++j)
+                        mma_ts(tmem_base + ((j & 1) ? G_OB_COL : G_OA_COL), pcol + (uint32_t)(8 * j), vdesc + (uint64_t)(128 * j),
+                               kGitIdescPV, (c != 0 || j >= 2) ? 1u : 0u);
                     tcgen05_commit(kv_empty(st));                            // K and V of this chunk consumed
+                    tcgen05_commit(pv_done);                                 // O holds chunks <= c (a later rescale may touch it)
                     if (c == n_chunks - 1) tcgen05_commit(o_full);
                 }
             }
@@ -228,13 +250,12 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                 const int limit = c < n_chunks_vis ? min(GK_CHUNK, n_vis - c * GK_CHUNK)
                                              : min(GK_CHUNK, txt_pos - (c - n_chunks_vis) * GK_CHUNK + 1);
                 const bool full = __all_sync(0xffffffffu, limit == GK_CHUNK);        // warp-uniform: the unmasked fast path
-                mbar_wait(s_full, ch & 1u);
+                const uint32_t scol = trow + (ch & 1u) * GK_CHUNK;                     // this chunk's S buffer
+                mbar_wait(s_full((int)(ch & 1u)), (ch >> 1) & 1u);
                 tcgen05_fence_after();
                 uint32_t v[GK_CHUNK];
-                tmem_ld32(trow, v);
-                tmem_ld32(trow + 32u, v + 32);
-                tmem_ld32(trow + 64u, v + 64);
-                tmem_ld32(trow + 96u, v + 96);
+                tmem_ld32(scol, v);
+                tmem_ld32(scol + 32u, v + 32);
                 tmem_wait_ld();
                 float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (full) {
@@ -256,6 +277,10 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                     if (move) m_ref = cmax;
                     l *= alpha;
                     if (c != 0) {                                                   // O_a | O_b hold P V of chunks < c: rescale this row
+                        // S of this chunk was issued BEFORE P V of chunk c-1: wait for that P V explicitly.  The barrier cannot be
+                        // more than one phase ahead (P V of chunk c needs this thread's arrival below), so the parity is unambiguous
+                        mbar_wait(pv_done, (ch - 1u) & 1u);
+                        tcgen05_fence_after();
 #pragma unroll
                         for (int piece = 0; piece < 4; ++piece) {
                             uint32_t o[32];
@@ -268,10 +293,10 @@ attention_git_tcgen05_kernel(const __grid_constant__ CUtensorMap map_qkv, const 
                         }
                     }
                 }
-                l += full ? git_exp_and_store<false>(v, m_ref, limit, trow) : git_exp_and_store<true>(v, m_ref, limit, trow);
+                l += full ? git_exp_and_store<false>(v, m_ref, limit, scol) : git_exp_and_store<true>(v, m_ref, limit, scol);
                 tmem_wait_st();
                 tcgen05_fence_before();
-                mbar_arrive(p_full);
+                mbar_arrive(p_full((int)(ch & 1u)));
             }
             // ---- epilogue: this warp's 32 query rows of this head
             mbar_wait(o_full, it & 1u);
@@ -339,14 +364,15 @@ int launch_attention_git_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, l
     const long long n_items = (long long)n_samples * kHeads * (n_qtiles_vis + n_qtiles_txt);
     if (n_items == 0) return 0;
     SASVQA_REQUIRE(n_items < 2147483647LL, "too many attention work items for one launch");
-    CUtensorMap map_qkv, map_out;
+    CUtensorMap map_qkv, map_kv, map_out;
     int rc = make_tensor_map_bf16_kmajor(&map_qkv, qkv, (uint64_t)rows_total, kQkv, 128);
     if (rc) return rc;
+    if ((rc = make_tensor_map_bf16_kmajor(&map_kv, qkv, (uint64_t)rows_total, kQkv, GK_CHUNK))) return rc;
     if ((rc = make_tensor_map_out(&map_out, out, (uint64_t)rows_total, kHidden, 0))) return rc;
     static SmemAttrCache smem_attr;
     if ((rc = smem_attr.ensure(attention_git_tcgen05_kernel, G_SMEM))) return rc;
     const int grid = (int)std::min<long long>(n_items, 2LL * num_sms);
-    attention_git_tcgen05_kernel<<<grid, G_THREADS, G_SMEM, s>>>(map_qkv, map_out, out, n_vis, L, (long long)n_samples * n_vis,
+    attention_git_tcgen05_kernel<<<grid, G_THREADS, G_SMEM, s>>>(map_qkv, map_kv, map_out, out, n_vis, L, (long long)n_samples * n_vis,
                                                                  n_qtiles_vis, n_qtiles_txt, n_chunks_vis, (int)n_items);
     SASVQA_CUDA_CHECK(cudaGetLastError());
     count_launch();
