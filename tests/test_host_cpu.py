@@ -331,3 +331,65 @@ def test_git_decoder_state_dict_flattening_and_hf_key_order():
     flat, vocab, n_layers = vqa.flatten_git_decoder_state_dict(model.state_dict())
     assert (vocab, n_layers) == (64, 2)
     assert flat.numel() == _capi.lib().sasvqa_git_decoder_num_params(64, 2)
+
+
+def test_h264_pcm_writer_is_parseable():
+    """tests/h264_pcm.py (the NVDEC known-answer stream) checked WITHOUT a decoder: NAL framing, emulation prevention, the
+    SPS fields a parser reads the frame size from, and the raw samples of the first macroblock of every picture."""
+    import h264_pcm
+    rng = np.random.RandomState(3)
+    T, H, W = 3, 32, 48
+    y = rng.randint(0, 256, (T, H, W)).astype(np.uint8)
+    u = rng.randint(0, 256, (T, H // 2, W // 2)).astype(np.uint8)
+    v = rng.randint(0, 256, (T, H // 2, W // 2)).astype(np.uint8)
+    y[0, :16, :16] = 0                                   # a macroblock of zeros: must be escaped (00 00 03)
+    stream = h264_pcm.encode_i_pcm(y, u, v)
+    nals = [n for n in stream.split(b"\x00\x00\x00\x01") if n]
+    assert [n[0] & 0x1F for n in nals] == [7, 8] + [5] * T            # SPS, PPS, one IDR slice per frame
+    for n in nals:                                       # no start-code emulation inside a NAL
+        assert re.search(rb"\x00\x00[\x00-\x02]", n) is None
+
+    def rbsp(nal):                                       # strip the header byte and the emulation-prevention bytes
+        out, zeros = bytearray(), 0
+        for b in nal[1:]:
+            if zeros >= 2 and b == 3:
+                zeros = 0
+                continue
+            out.append(b)
+            zeros = zeros + 1 if b == 0 else 0
+        return bytes(out)
+
+    class Bits:
+        def __init__(self, data):
+            self.d, self.p = data, 0
+
+        def u(self, n):
+            val = 0
+            for _ in range(n):
+                val = (val << 1) | ((self.d[self.p >> 3] >> (7 - (self.p & 7))) & 1)
+                self.p += 1
+            return val
+
+        def ue(self):
+            z = 0
+            while self.u(1) == 0:
+                z += 1
+            return (1 << z) - 1 + (self.u(z) if z else 0)
+
+    sps = Bits(rbsp(nals[0]))
+    assert sps.u(8) == 66 and sps.u(8) == 0xC0 and sps.u(8) == 40            # Baseline, level 4.0
+    assert [sps.ue() for _ in range(4)] == [0, 0, 2, 1]                     # sps id, log2_max_frame_num-4, poc type 2, ref frames
+    assert sps.u(1) == 0
+    assert (sps.ue() + 1) * 16 == W and (sps.ue() + 1) * 16 == H
+    for t in range(T):
+        sl = Bits(rbsp(nals[2 + t]))
+        assert sl.ue() == 0 and sl.ue() == 7 and sl.ue() == 0 and sl.u(4) == 0 and sl.ue() == t     # first_mb, I slice, pps, frame_num, idr_pic_id
+        sl.u(2)                                                                # dec_ref_pic_marking flags
+        assert sl.ue() == 0 and sl.ue() == 1                                   # slice_qp_delta (se(0) reads as ue 0), deblocking off
+        assert sl.ue() == 25                                                   # mb_type I_PCM
+        while sl.p & 7:
+            assert sl.u(1) == 0                                                # pcm_alignment_zero_bit
+        first_mb = np.frombuffer(sl.d[sl.p >> 3:(sl.p >> 3) + 256], dtype=np.uint8).reshape(16, 16)
+        np.testing.assert_array_equal(first_mb, y[t, :16, :16])
+    rgb = h264_pcm.yuv_to_rgb_bt601(y, u, v)
+    assert rgb.shape == (T, H, W, 3) and rgb.dtype == np.uint8
